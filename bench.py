@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the Blurry-Edges render -> fold -> depth hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs B]
+
+A step = one pass B (blurry_edges_test.py:81-100: render both images with shared ridge colours, sharpened and
+refocused renders, boundary, depth mask/map, five folds) over one batch of synthetic 147x147 image pairs
+(config[1] of BASELINE.json: 64 pairs = 262144 patches per GPU).  N > 1 (torchrun, one rank per GPU): every rank
+processes its own batch of pairs (weak scaling, no data-path collective); time = max over ranks.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
+C-ABI entry point with H2D/D2H copies inside the timed region, `roofline` the HBM roofline of the dominant kernel
+(be_run_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
+`--impl reference` times the CPU port of the reference's eager PyTorch path (the reference itself is Python and is
+not present on the GPU box; oracle/be_oracle.py is pinned to it by tests/golden)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+S, R, STRIDE = 147, 21, 2
+HP = (S - R) // STRIDE + 1
+L = HP * HP
+METRIC = 'patches/sec render+fold+depth (inference pass B)'
+UNIT = 'patches/s'
+# algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
+# params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
+ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def make_inputs(B, seed):
+    import synth
+    from oracle import be_oracle as O   # only restore_global(): builds the synthetic parameters, not the measured path
+    est = O.restore_global(synth.raw_global(B, L, seed=seed)).contiguous()
+    img = synth.image_pairs(B, S, S, seed=seed + 1).permute(0, 1, 4, 2, 3).contiguous()   # planar [B,2,3,H,W]
+    return est, img
+
+
+def cpu_reference_step(est, img, threads):
+    """The reference's eager fp32 CPU path for pass B, restated (oracle/be_oracle.py, trace-formula inverse as in
+    utils/postprocessing_loss.py:104-112); like the reference helper it handles one pair per call."""
+    from oracle import be_oracle as O
+    g, cam = O.Geometry(H=S, W=S), O.Camera()
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        for b in range(est.shape[0]):
+            O.inference(est[b:b + 1], img[b:b + 1], g, cam, 10.39, None, trace_form=True)
+
+
+def time_cpu(pairs, reps, threads):
+    est, img = make_inputs(pairs, seed=900)
+    cpu_reference_step(est[:1], img[:1], threads)   # warm-up
+    best = float('inf')
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(est, img, threads)
+        best = min(best, time.perf_counter() - t0)
+    return pairs * L / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs = args.ref_pairs
+    est, img = make_inputs(pairs, seed=900)
+    for _ in range(args.warmup):
+        cpu_reference_step(est[:1], img[:1], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(est, img, threads)
+    dt = time.perf_counter() - t0
+    val = args.steps * pairs * L / dt
+    out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': f'pass B on {S}x{S} pairs, R={R}, stride={STRIDE}; each step = {pairs} pairs ({pairs * L} patches), '
+                                  'a bounded sample of the 64-pair batch'},
+           'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                            'sample': f'{pairs} pairs/step x {args.steps} steps, torch {torch.__version__} eager fp32 CPU, '
+                                      'oracle/be_oracle.py restatement of the reference (one pair per call, as the reference helper)'},
+           'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from blurry_edges_b200 import Context, _lib, make_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU port')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    B = args.pairs
+    est_h, img_h = make_inputs(B, seed=100 + rank)
+    est_h, img_h = est_h.pin_memory(), img_h.pin_memory()
+    est, img = est_h.to(dev), img_h.to(dev)
+    ctx = Context(make_config(H=S, W=S, max_batch=B), dev)
+    layout = _lib.planar_layout(S, S)
+    out = ctx.alloc_outputs(B, True)
+    host_out = ctx.host_render_fold(est_h, img_h, layout)          # allocates pinned outputs + staging (untimed)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        ctx.render_fold(est, img, layout, out=out)
+
+    ctx.set_timing(True)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    n0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern = []
+    with ClockSampler(local_rank) as clk:
+        t_wall = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()                                          # L2 flush between timed iterations (untimed)
+            a.record()
+            step()
+            b.record()
+            kern.append(ctx.last_timing())                         # waits for this step's last kernel
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    launches = _lib.launch_count() - n0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ctx.set_timing(False)
+
+    # end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H of the maps
+    for _ in range(max(1, args.warmup // 2)):
+        ctx.host_render_fold(est_h, img_h, layout, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.host_render_fold(est_h, img_h, layout, out=host_out)   # synchronises internally
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        return
+    patches = B * L * world
+    value = patches * args.steps / (dev_ms / 1e3)
+    e2e = patches * args.steps / (e2e_ms / 1e3)
+    run_ms = sum(k[2] for k in kern) / len(kern)
+    shares = [sum(k[i] for k in kern) / len(kern) for i in range(4)]
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_PATCH * B * L / (run_ms / 1e3) / 1e9
+    res = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+           'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': f'inference pass B (render+fold+depth), {B} synthetic {S}x{S} pairs per GPU = {B * L} patches/step/GPU, '
+                                  f'R={R}, stride={STRIDE}, densify=None (BASELINE.json configs[1])',
+                      'l2': 'flushed between timed iterations (256 MiB write, untimed); working set 217 MB > 126 MB L2',
+                      'sharding': 'one batch per rank, no data-path collective'},
+           'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(B * (L * 12 + 6 * S * S) * 4),
+                   'd2h_bytes_per_step': int(B * 16 * S * S * 4), 'ms_per_step': e2e_ms / args.steps,
+                   'api': 'be_host_render_fold (pinned host buffers, synchronous)'},
+           'gpu_launches': int(launches),
+           'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                        'traffic': None, 'kernel': 'be_run_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
+                        'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
+                        'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
+                                'see profiles/ for pipe utilisation'},
+           'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run_kernel': shares[2], 'be_normalise_kernel': shares[3]},
+           'clocks': clk.summary(), 'wall_s_timed_region': t_wall}
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, sec = time_cpu(args.ref_pairs, 2, cores)
+        res['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                               'sample': f'{args.ref_pairs} of the {B} pairs (best of 2, {sec:.2f} s), torch eager fp32 CPU port of the '
+                                         'reference (oracle/be_oracle.py), one pair per call'}
+        try:
+            from oracle import be_oracle as O, hostmath
+            g, cam = O.Geometry(H=S, W=S), O.Camera()
+            e2, i2 = make_inputs(8, seed=901)
+            hostmath.render_fold(e2[:1], i2[:1], g, cam)
+            t0 = time.perf_counter()
+            hostmath.render_fold(e2, i2, g, cam)
+            res['cpu_baseline']['c_port_openmp'] = {'value': 8 * L / (time.perf_counter() - t0), 'unit': UNIT,
+                                                    'note': 'oracle/be_hostmath.cpp: the kernels\' arithmetic on host cores, OpenMP over pairs'}
+        except Exception as e:  # the C port is optional evidence
+            res['cpu_baseline']['c_port_openmp'] = {'error': str(e)[:100]}
+    print(json.dumps(res), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pairs', type=int, default=64, help='image pairs per GPU per step (BASELINE configs[1]: 64)')
+    ap.add_argument('--ref-pairs', type=int, default=4, help='pairs per step of the CPU reference sample')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

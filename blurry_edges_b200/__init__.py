@@ -1,0 +1,10 @@
+"""blurry_edges_b200 - B200-native (sm_100a) render -> fold -> depth path of Blurry-Edges.
+
+Only what the hot path needs lives here: csrc/ (CUDA kernels + C ABI), the ctypes binding (_lib) and the
+host-side mirror of the reference's helper classes.  Importing the package never touches a GPU; constructing
+any of its classes on a machine without the built library or without a CUDA device raises."""
+from . import _lib
+from ._lib import BlurryEdgesError, Context, make_config
+from .fused import PostProcessFused
+
+__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', '_lib']

@@ -1,0 +1,235 @@
+"""ctypes binding of libblurry_edges_b200.so (C ABI in include/blurry_edges_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or a call fails, an exception
+is raised.  PyTorch is used only for device memory and streams; tensors cross the boundary as raw
+device pointers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libblurry_edges_b200.so')
+
+PARAMS_RESTORED12, PARAMS_RAW12, PARAMS_LOCAL10, PARAMS_LOCALRAW10 = 0, 1, 2, 3
+
+
+class BeConfig(C.Structure):
+    _fields_ = [('R', C.c_int32), ('stride', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('w', C.c_double), ('alpha_lambda', C.c_double),
+                ('cam_s', C.c_double), ('cam_rho_1', C.c_double), ('cam_rho_2', C.c_double),
+                ('cam_sigma_cam', C.c_double), ('cam_pixel_pitch', C.c_double), ('cam_mag', C.c_double),
+                ('rho_prime', C.c_double), ('max_batch', C.c_int32)]
+
+
+class BeImageLayout(C.Structure):
+    _fields_ = [('sb', C.c_int64), ('sm', C.c_int64), ('sc', C.c_int64), ('sy', C.c_int64), ('sx', C.c_int64)]
+
+
+class BlurryEdgesError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_SIGS = {
+    'be_abi_version': (C.c_int, []),
+    'be_last_error': (C.c_char_p, []),
+    'be_launch_count': (C.c_int64, []),
+    'be_ctx_create': (C.c_int, [C.POINTER(_P), C.POINTER(BeConfig)]),
+    'be_ctx_destroy': (C.c_int, [_P]),
+    'be_ctx_workspace_bytes': (C.c_int64, [_P]),
+    'be_ctx_constants': (C.c_int, [_P, C.POINTER(C.c_double)]),
+    'be_derive_constants': (C.c_int, [C.POINTER(BeConfig), C.POINTER(C.c_double)]),
+    'be_ctx_set_timing': (C.c_int, [_P, C.c_int32]),
+    'be_ctx_last_timing': (C.c_int, [_P, C.POINTER(C.c_float)]),
+    'be_cover_count': (C.c_int, [_P, _P, _P]),
+    'be_refold_image': (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    'be_colors_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, _P, _P]),
+    'be_render_fold_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
+                                     _P, _P, _P, _P, _P, _P, _P, _P]),
+    'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
+                                      _P, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names declared in include/blurry_edges_b200.h that the library must export."""
+    return list(_SIGS)
+
+
+def load():
+    """dlopen the library (building is the job of blurry_edges_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BlurryEdgesError(f'{LIB_PATH} is missing: run `python -m blurry_edges_b200.build` '
+                               '(there is no CPU or PyTorch fallback for this path)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BlurryEdgesError(load().be_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(load().be_launch_count())
+
+
+def make_config(R=21, stride=2, H=147, W=147, w=1.0, alpha_lambda=5e-3, cam=None, mag=4.0, rho_prime=10.39,
+                max_batch=1) -> BeConfig:
+    cam = cam or {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
+    return BeConfig(R, stride, H, W, w, alpha_lambda, cam['s'], cam['rho_1'], cam['rho_2'], cam['sigma_cam'],
+                    cam['pixel_pitch'], mag, rho_prime, max_batch)
+
+
+def derive_constants(cfg: BeConfig):
+    out = (C.c_double * 8)()
+    check(load().be_derive_constants(C.byref(cfg), out))
+    return list(out)
+
+
+def _ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise BlurryEdgesError(f'expected a contiguous float32 CUDA tensor, got {t.dtype} on {t.device}, '
+                               f'contiguous={t.is_contiguous()}')
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def planar_layout(H, W) -> BeImageLayout:
+    """[B,2,3,H,W] (or [M,3,H,W] with sm unused)."""
+    return BeImageLayout(6 * H * W, 3 * H * W, H * W, W, 1)
+
+
+def single_planar_layout(H, W) -> BeImageLayout:
+    """[M,3,H,W]: one image per batch index."""
+    return BeImageLayout(3 * H * W, 0, H * W, W, 1)
+
+
+def channels_last_layout(H, W) -> BeImageLayout:
+    """dataset-native [B,2,H,W,3] (data/dataset.py:63)."""
+    return BeImageLayout(6 * H * W, 3 * H * W, 1, 3 * W, 3)
+
+
+class Context:
+    """Owns one be_ctx (geometry + camera + HBM workspace) on one device."""
+
+    def __init__(self, cfg: BeConfig, device):
+        self.lib = load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise BlurryEdgesError(f'blurry_edges_b200 runs on CUDA devices only (got {self.device}); no CPU fallback')
+        self.cfg = cfg
+        self.h = _P()
+        with torch.cuda.device(self.device):
+            check(self.lib.be_ctx_create(C.byref(self.h), C.byref(cfg)))
+        c = (C.c_double * 8)()
+        check(self.lib.be_ctx_constants(self.h, c))
+        (self.numerator, self.denominator_constant, self.denominator_factor_root, self.denominator_factor,
+         self.intercept, self.lambda_ridge) = list(c)[:6]
+        self.Hp, self.Wp = int(c[6]), int(c[7])
+        self.L = self.Hp * self.Wp
+
+    def close(self):
+        if getattr(self, 'h', None) and self.h.value:
+            self.lib.be_ctx_destroy(self.h)
+            self.h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def max_batch(self):
+        return self.cfg.max_batch
+
+    def workspace_bytes(self):
+        return int(self.lib.be_ctx_workspace_bytes(self.h))
+
+    def set_timing(self, enable=True):
+        with torch.cuda.device(self.device):
+            check(self.lib.be_ctx_set_timing(self.h, int(enable)))
+
+    def last_timing(self):
+        """ms of (memset, setup kernel, run kernel, normalise kernel) of the last render_fold call."""
+        ms = (C.c_float * 4)()
+        with torch.cuda.device(self.device):
+            check(self.lib.be_ctx_last_timing(self.h, ms))
+        return list(ms)
+
+    # ---- device-pointer entry points ---------------------------------------------------
+    def cover_count(self):
+        out = torch.empty(self.cfg.H, self.cfg.W, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_cover_count(self.h, _ptr(out), _stream(self.device)))
+        return out
+
+    def refold(self, unfolded: torch.Tensor):
+        M = unfolded.numel() // (3 * self.cfg.R * self.cfg.R * self.L)
+        img = torch.empty(M, 3, self.cfg.H, self.cfg.W, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_refold_image(self.h, _ptr(unfolded), M, _ptr(img), _stream(self.device)))
+        return img
+
+    def colors(self, est: torch.Tensor, img: torch.Tensor, layout: BeImageLayout, param_mode=PARAMS_LOCAL10):
+        M = est.shape[0]
+        out = torch.empty(M, 3, 3, self.Hp, self.Wp, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_colors_fwd(self.h, _ptr(est), param_mode, _ptr(img), C.byref(layout), M, _ptr(out),
+                                         _stream(self.device)))
+        return out
+
+    def render_fold(self, est: torch.Tensor, img: torch.Tensor, layout: BeImageLayout, densify_w=False,
+                    param_mode=PARAMS_RESTORED12, out=None, want_thresholded=True):
+        B, H, W = est.shape[0], self.cfg.H, self.cfg.W
+        if out is None:
+            out = self.alloc_outputs(B, want_thresholded)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_render_fold_fwd(self.h, _ptr(est), param_mode, _ptr(img), C.byref(layout), B, int(densify_w),
+                                              *[_ptr(t) for t in out], *([None] if len(out) == 6 else []),
+                                              _stream(self.device)))
+        return out
+
+    def alloc_outputs(self, B, want_thresholded=True):
+        H, W, kw = self.cfg.H, self.cfg.W, dict(device=self.device, dtype=torch.float32)
+        out = [torch.empty(B, 2, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw),
+               torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
+        if want_thresholded:
+            out.append(torch.empty(B, H, W, **kw))
+        return out
+
+    # ---- host-buffer entry point (numpy / pinned host tensors in, numpy out) ------------
+    def host_render_fold(self, est, img, layout: BeImageLayout, densify_w=False, param_mode=PARAMS_RESTORED12, out=None):
+        """est, img: CPU float32 contiguous torch tensors (ideally pinned).  Returns 7 CPU tensors."""
+        B, H, W = est.shape[0], self.cfg.H, self.cfg.W
+        for t in (est, img):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise BlurryEdgesError('host_render_fold expects contiguous float32 CPU tensors')
+        if out is None:
+            pin = dict(dtype=torch.float32, pin_memory=True)
+            out = [torch.empty(B, 2, 3, H, W, **pin), torch.empty(B, 3, H, W, **pin), torch.empty(B, 3, H, W, **pin),
+                   torch.empty(B, 1, H, W, **pin), torch.empty(B, H, W, **pin), torch.empty(B, H, W, **pin),
+                   torch.empty(B, H, W, **pin)]
+        with torch.cuda.device(self.device):
+            check(self.lib.be_host_render_fold(self.h, C.c_void_p(est.data_ptr()), param_mode, C.c_void_p(img.data_ptr()),
+                                               C.byref(layout), B, int(densify_w),
+                                               *[C.c_void_p(t.data_ptr()) for t in out]))
+        return out

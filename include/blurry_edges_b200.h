@@ -1,0 +1,108 @@
+/* blurry_edges_b200 - C ABI of the B200-native (sm_100a) Blurry-Edges render -> fold -> depth path.
+ *
+ * The reference (guo-research-group/Blurry-Edges) is pure Python and has no FFI; its boundary for
+ * this path is the set of Python classes the scripts subclass.  Each entry
+ * point below names the reference code it replaces (paths relative to the reference repo).  The
+ * Python mirror in blurry_edges_b200/ binds these with ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; be_last_error() gives the message
+ *   - all tensors are fp32, dense, row-major; "dev" pointers live in HBM of the current device
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous
+ *     on it unless their name starts with be_host_
+ *   - inputs are borrowed and never written; outputs are caller-allocated
+ *   - patch index l = py * Wp + px;  Hp = (H-R)/stride + 1, Wp likewise; R <= 21
+ */
+#ifndef BLURRY_EDGES_B200_H
+#define BLURRY_EDGES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BE_ABI_VERSION 1
+
+/* how a patch's parameter vector is encoded (see be_math.cuh) */
+#define BE_PARAMS_RESTORED12 0   /* xy, wrapped angles, eta coefficients: what blurry_edges_test.py:135-138 builds */
+#define BE_PARAMS_RAW12 1        /* raw GlobalStage output: restore = global_training.py:141-145 */
+#define BE_PARAMS_LOCAL10 2      /* xy, wrapped angles, 2 eta coefficients: blurry_edges_test.py:123-127 */
+#define BE_PARAMS_LOCALRAW10 3   /* raw LocalStage output, angles wrapped inside: local_training.py:33 */
+
+typedef struct be_config {
+    int32_t R, stride, H, W;          /* utils/args.py:9-11,40  (defaults 21, 2, 147, 147) */
+    double w, alpha_lambda;           /* utils/args.py:12-13 (python floats) */
+    /* utils/args.py:14-15 camera (DepthEtas.__init__, utils/depth_etas.py:4-21) */
+    double cam_s, cam_rho_1, cam_rho_2, cam_sigma_cam, cam_pixel_pitch, cam_mag;
+    double rho_prime;                 /* utils/args.py:81 */
+    int32_t max_batch;                /* largest number of image PAIRS per call; sizes the workspace */
+} be_config;
+
+/* element strides of an image tensor: value(b, m, c, y, x) = base[b*sb + m*sm + c*sc + y*sy + x*sx]
+ * (b = pair or image index, m = image within the pair).  Planar [B,2,3,H,W]: {6HW, 3HW, HW, W, 1};
+ * dataset-native [B,2,H,W,3] (data/dataset.py:63): {6HW, 3HW, 1, 3W, 3}. */
+typedef struct be_image_layout { int64_t sb, sm, sc, sy, sx; } be_image_layout;
+
+typedef struct be_ctx be_ctx;
+
+int be_abi_version(void);
+const char* be_last_error(void);
+
+/* PostProcessGlobalBase.__init__ + DepthEtas.__init__ (utils/postprocessing_loss.py:8-20,131-143,
+ * utils/depth_etas.py:4-21): validates geometry, derives constants, allocates the HBM workspace. */
+int be_ctx_create(be_ctx** out, const be_config* cfg);
+int be_ctx_destroy(be_ctx* ctx);
+int64_t be_ctx_workspace_bytes(const be_ctx* ctx);
+/* derived constants, for the Python mirror's attributes: out[0..7] = numerator, denominator_constant,
+ * denominator_factor_root, denominator_factor, intercept, lambda_ridge, Hp, Wp */
+int be_ctx_constants(const be_ctx* ctx, double* out8);
+/* same constants from a config alone; pure host arithmetic, usable without a GPU */
+int be_derive_constants(const be_config* cfg, double* out8);
+
+/* num_patches of PostProcessGlobalBase (utils/postprocessing_loss.py:139-143), closed form. out [H,W]. */
+int be_cover_count(be_ctx* ctx, float* dev_out, void* stream);
+
+/* Undo nn.Unfold (blurry_edges_test.py:119-120): unfolded [M,3,R,R,Hp,Wp] -> image [M,3,H,W]. */
+int be_refold_image(be_ctx* ctx, const float* dev_unfolded, int32_t M, float* dev_image, void* stream);
+
+/* Pass A: PostProcess.forward(..., colors_only=True) (blurry_edges_test.py:81-92, get_colors :19-28;
+ * global_data_pre_cal.py:39-47).  est [M,L,10] (param_mode LOCAL10 or LOCALRAW10), one image per est row
+ * (layout.sm unused) -> colors [M,3(channel),3(wedge),Hp,Wp]. */
+int be_colors_fwd(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
+                  const be_image_layout* layout, int32_t M, float* dev_colors, void* stream);
+
+/* Pass B: PostProcess.forward(..., colors_only=False) (blurry_edges_test.py:30-100) for B pairs:
+ * render both images with shared ridge colours, sharpened + refocused renders, boundary, depth mask/map,
+ * and the five folds of utils/postprocessing_loss.py:151-173 - without materialising unfolded tensors.
+ * est [B,L,12]; outputs image [B,2,3,H,W], sharp [B,3,H,W], refoc [B,3,H,W], bndry [B,1,H,W],
+ * depth [B,H,W], conf [B,H,W].  densify_w != 0 selects the `--densify w` mask rule (:47-50).
+ * depth_thresholded (may be NULL): where(conf > thres, depth, 0) with thres = 0 ('w') / 0.05 (:109-112,144). */
+int be_render_fold_fwd(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
+                       const be_image_layout* layout, int32_t B, int32_t densify_w,
+                       float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry,
+                       float* dev_depth, float* dev_conf, float* dev_depth_thresholded, void* stream);
+
+/* Host-buffer form of pass B (what a ctypes binding on the reference side calls with numpy arrays):
+ * copies est/img to HBM, runs be_render_fold_fwd, copies the six maps (+thresholded depth) back, and
+ * synchronises.  Same shapes as above; img is planar [B,2,3,H,W] or dataset-native via `layout`. */
+int be_host_render_fold(be_ctx* ctx, const float* est, int32_t param_mode, const float* img,
+                        const be_image_layout* layout, int32_t B, int32_t densify_w,
+                        float* image, float* sharp, float* refoc, float* bndry, float* depth, float* conf,
+                        float* depth_thresholded);
+
+/* Measurement hook: with timing enabled, be_render_fold_fwd brackets each of its four device operations with CUDA
+ * events on the caller's stream; be_ctx_last_timing waits for the last call and returns their durations in ms:
+ * ms4 = {accumulator memset, be_setup_kernel, be_run_kernel, be_normalise_kernel}. */
+int be_ctx_set_timing(be_ctx* ctx, int32_t enable);
+int be_ctx_last_timing(be_ctx* ctx, float* ms4);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t be_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
