@@ -223,6 +223,7 @@ int be_refold_image(be_ctx* c, const float* dev_unfolded, int32_t M, float* dev_
 int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
                   int32_t M, float* dev_colors, void* stream) {
     if (check_ctx(c) || check_layout(layout)) return 1;
+    if (M == 0) return 0;
     BE_REQUIRE(dev_est && dev_img && dev_colors, "null pointer");
     BE_REQUIRE(param_mode == BE_PARAMS_LOCAL10 || param_mode == BE_PARAMS_LOCALRAW10, "be_colors_fwd takes 10-parameter patches");
     BE_REQUIRE(M >= 0 && M <= 2 * c->cfg.max_batch, "M=%d exceeds 2*max_batch=%d", M, 2 * c->cfg.max_batch);
@@ -244,6 +245,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
                        int32_t B, int32_t densify_w, float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry,
                        float* dev_depth, float* dev_conf, float* dev_depth_thr, void* stream) {
     if (check_ctx(c) || check_layout(layout)) return 1;
+    if (B == 0) return 0;
     BE_REQUIRE(dev_est && dev_img && dev_image && dev_sharp && dev_refoc && dev_bndry && dev_depth && dev_conf, "null pointer");
     BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_render_fold_fwd takes 12-parameter patches");
     BE_REQUIRE(B >= 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
@@ -275,6 +277,7 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
                         int32_t B, int32_t densify_w, float* image, float* sharp, float* refoc, float* bndry, float* depth,
                         float* conf, float* depth_thr) {
     if (check_ctx(c) || check_layout(layout)) return 1;
+    if (B == 0) return 0;
     BE_REQUIRE(est && img && image && sharp && refoc && bndry && depth && conf, "null pointer");
     BE_REQUIRE(B >= 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
     if (B == 0) return 0;

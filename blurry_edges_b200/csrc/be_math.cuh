@@ -247,3 +247,141 @@ BE_HD void be_solve_colors(const float* S, float lam, double* Minv, float* C) {
         C[6 + ch] = (float)(Minv[2] * b0 + Minv[4] * b1 + Minv[5] * b2);
     }
 }
+
+// ==========================================================================================
+// Backward pieces (closed forms of SURVEY.md section 7; every folded target of the loss is detached in the reference,
+// global_training.py:95,101,106, so the backward pass is purely per patch).
+// ==========================================================================================
+#define BE_INV_SQRT_PI 0.564189584f
+#define BE_LN10 2.30258509f
+
+struct BePatchGrad {      // per-patch chain-rule scalars
+    float deta_dcoef[4];  // d eta_q / d coef_q   (:88-89)
+    float dz_deta[4];     // dz1/deta0, dz1/deta2, dz2/deta1, dz2/deta3   (utils/depth_etas.py:23-34)
+    float xy_scale, ang_scale;   // d(restored)/d(raw): 3 and pi for RAW12 (global_training.py:142-143), 1 otherwise
+};
+
+// d h / d dist and d h / d eta for h = 0.5 (1 + erf(dist * inv_eta)), inv_eta = 1/(sqrt2 eta)
+BE_HD void be_h_grad(float dist, float inv_eta, float* dh_dd, float* dh_deta) {
+    const float t = dist * inv_eta;
+    const float e = BE_INV_SQRT_PI * be_exp2(-(t * t) * 1.44269504f);
+    *dh_dd = e * inv_eta;
+    *dh_deta = -e * t * (BE_SQRT2_F * inv_eta);     // 1/eta = sqrt2 * inv_eta
+}
+
+BE_HD void be_depth_grad(const BeCam& cam, float e1, float e2, float* dz1, float* dz2) {
+    const float c = cam.intercept;
+    const float c1 = -cam.sin_w * e1 + cam.cos_w * (e2 - c);
+    const float c2 = -cam.sin_m * (e1 - c) + cam.cos_m * e2;
+    const float c3 = -cam.sin_w * (e1 - c) + cam.cos_w * e2;
+    const float half = (e1 + e2 - c) * 0.5f;
+    float a, b, a1, a2, b1, b2;     // a,b and their partials wrt e1,e2
+    if (c1 > 0.0f) { a = half; b = c + half; a1 = a2 = b1 = b2 = 0.5f; }
+    else if (c2 > 0.0f) { a = c + (e1 - e2 - c) * 0.5f; b = (e2 - e1 + c) * 0.5f; a1 = 0.5f; a2 = -0.5f; b1 = -0.5f; b2 = 0.5f; }
+    else if (c3 < 0.0f) { a = c + half; b = half; a1 = a2 = b1 = b2 = 0.5f; }
+    else { a = e1; b = e2; a1 = 1.0f; a2 = 0.0f; b1 = 0.0f; b2 = 1.0f; }
+    const float den = cam.k_fac * (a * a - b * b) + cam.k_const;
+    const float f = -cam.numerator * cam.k_fac * 2.0f / (den * den);     // dz/d(a^2-b^2) * 2
+    *dz1 = f * (a * a1 - b * b1);
+    *dz2 = f * (a * a2 - b * b2);
+}
+
+BE_HD void be_patch_grad_setup(const float* p, int mode, const BeCam& cam, const BePatch& P, BePatchGrad& G) {
+    const bool raw12 = (mode == BE_PARAMS_RAW12);
+    const int neta = (mode == BE_PARAMS_LOCAL10 || mode == BE_PARAMS_LOCALRAW10) ? 2 : 4;
+    for (int k = 0; k < 4; ++k) {
+        if (k < neta) {
+            const float e = raw12 ? p[8 + k] + 0.5f : p[8 + k];
+            G.deta_dcoef[k] = P.eta[k] * (BE_LN10 * 4.0f * BE_INV_SQRT_PI) * be_exp2(-(e * e) * 1.44269504f);
+        } else G.deta_dcoef[k] = 0.0f;
+    }
+    if (neta == 4) {
+        be_depth_grad(cam, P.eta[0], P.eta[2], &G.dz_deta[0], &G.dz_deta[1]);
+        be_depth_grad(cam, P.eta[1], P.eta[3], &G.dz_deta[2], &G.dz_deta[3]);
+    } else { G.dz_deta[0] = G.dz_deta[1] = G.dz_deta[2] = G.dz_deta[3] = 0.0f; }
+    G.xy_scale = raw12 ? 3.0f : 1.0f;
+    G.ang_scale = raw12 ? BE_PI_F : 1.0f;
+}
+
+// Gradient of the signed distance of wedge k at one pixel w.r.t. (vertex x, vertex y, angle of edge A, angle of edge B),
+// scaled by g = dL/d dist_k and ADDED into acc[0..3].  Mirrors autograd through :52-84: min() routes to the smaller
+// |D| (ties split 1/2), abs() has sign(0) = 0, the cap branch is d/dd = d/r, d/da = w^2 a/r.
+BE_HD void be_wedge_backward(const BePatch& P, int k, float X, float Y, float w, float g, float* acc) {
+    const float dx = X - P.vx[k], dy = Y - P.vy[k];
+    const float f = P.flip[k];
+    float d[2], a[2], D[2];
+    for (int e = 0; e < 2; ++e) {
+        const float sn = P.sn[2 * k + e], cs = P.cs[2 * k + e];
+        d[e] = fmaf(cs, dy, -sn * dx);
+        a[e] = fmaf(cs, dx, sn * dy);
+        const float aw = a[e] * w;
+        const float cap = be_sqrt(fmaf(d[e], d[e], aw * aw));
+        D[e] = (a[e] < 0.0f) ? ((d[e] < 0.0f) ? -cap : cap) : d[e];
+    }
+    const bool in = (k == 0) ? ((f * D[0] > 0.0f) && (f * D[1] < 0.0f)) : ((f * D[0] >= 0.0f) && (f * D[1] <= 0.0f));
+    const float sg = g * (in ? f : -f);
+    const float absA = fabsf(D[0]), absB = fabsf(D[1]);
+    const float wA = (absA < absB) ? 1.0f : ((absA == absB) ? 0.5f : 0.0f);
+    for (int e = 0; e < 2; ++e) {
+        const float we = (e == 0) ? wA : 1.0f - wA;
+        if (we == 0.0f) continue;
+        const float absD = (e == 0) ? absA : absB;
+        float gd, ga;
+        if (a[e] < 0.0f) {
+            const float ir = (absD > 0.0f) ? 1.0f / absD : 0.0f;          // |D| = r on this branch
+            gd = sg * we * d[e] * ir;
+            ga = sg * we * (w * w) * a[e] * ir;
+        } else {
+            gd = sg * we * ((d[e] > 0.0f) ? 1.0f : ((d[e] < 0.0f) ? -1.0f : 0.0f));
+            ga = 0.0f;
+        }
+        const float sn = P.sn[2 * k + e], cs = P.cs[2 * k + e];
+        acc[0] += gd * sn - ga * cs;
+        acc[1] += -gd * cs - ga * sn;
+        acc[2 + e] += -gd * a[e] + ga * d[e];
+    }
+}
+
+// boundary map backward (blurry_edges_test.py:59-61): glb = dL/d lb -> adds to gd1, gd2
+BE_HD void be_boundary_backward(float d1, float d2, float lb, float glb, float* gd1, float* gd2) {
+    const float a1 = fabsf(d1), a2 = fabsf(d2);
+    const float k = -2.0f / (BE_DELTA * BE_DELTA);
+    if (d2 >= 0.0f) { *gd2 += glb * lb * k * d2; }
+    else if (a1 < a2) { *gd1 += glb * lb * k * a1 * ((d1 > 0.0f) ? 1.0f : ((d1 < 0.0f) ? -1.0f : 0.0f)); }
+    else { *gd2 += glb * lb * k * a2 * ((d2 > 0.0f) ? 1.0f : ((d2 < 0.0f) ? -1.0f : 0.0f)); }
+}
+
+// wedge values backward: gu = dL/du (3) -> dL/dh1, dL/dh2  (:93-95)
+BE_HD void be_wedges_backward(float h1, float h2, const float* gu, float* gh1, float* gh2) {
+    *gh1 = (1.0f - h2) * (gu[1] - gu[0]);
+    *gh2 = gu[2] - (1.0f - h1) * gu[0] - h1 * gu[1];
+}
+
+// Second solve of the ridge backward: V = Minv (A^T G), Ssym = V C^T + C V^T (packed 00,01,02,11,12,22).
+// AtG[3*w + c], C[3*w + c], V[3*w + c].
+BE_HD void be_backsolve(const double* Minv, const float* AtG, const float* C, float* V, float* Ssym) {
+    for (int c = 0; c < 3; ++c) {
+        const double b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
+        V[0 + c] = (float)(Minv[0] * b0 + Minv[1] * b1 + Minv[2] * b2);
+        V[3 + c] = (float)(Minv[1] * b0 + Minv[3] * b1 + Minv[4] * b2);
+        V[6 + c] = (float)(Minv[2] * b0 + Minv[4] * b1 + Minv[5] * b2);
+    }
+    int q = 0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            float s = 0.0f;
+            for (int c = 0; c < 3; ++c) s += V[3 * i + c] * C[3 * j + c] + C[3 * i + c] * V[3 * j + c];
+            Ssym[q++] = s;
+        }
+}
+
+// dL/du for one pixel of one image: G (3 channels) = dL/dP, y (3) = regression pixel, u (3) = wedges.
+BE_HD void be_ridge_backward_pixel(const float* G, const float* y, const float* u, const float* C, const float* V,
+                                   const float* Ssym, float* gu) {
+    const float S[9] = {Ssym[0], Ssym[1], Ssym[2], Ssym[1], Ssym[3], Ssym[4], Ssym[2], Ssym[4], Ssym[5]};
+    for (int w = 0; w < 3; ++w) {
+        float s = 0.0f;
+        for (int c = 0; c < 3; ++c) s += G[c] * C[3 * w + c] + y[c] * V[3 * w + c];
+        gu[w] = s - (S[3 * w] * u[0] + S[3 * w + 1] * u[1] + S[3 * w + 2] * u[2]);
+    }
+}

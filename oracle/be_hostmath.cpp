@@ -149,4 +149,270 @@ int behm_render_fold(const float* est, int param_mode, const float* img, const i
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Global-stage loss, forward + analytic backward (global_training.py:62-157), the algorithm of the CUDA loss kernel
+// written as plain loops.  Images are dataset-native channels-last [B,2,H,W,3]; deri [B,2,H-2,W-2,3].
+// terms7 = the seven UNWEIGHTED terms (means / masked mean), loss = sum gamma_k terms_k, grad = dloss/draw [B,L,12].
+// mode_local != 0: the local-stage loss (local_training.py:32-52): raw [B,10], images [B,R,R,3], one patch per sample,
+// terms = (colour, boundary localisation, smoothness), gammas = (1, beta_loc, beta_smth).
+// ------------------------------------------------------------------------------------------------------------------
+struct PatchWork {
+    std::vector<float> d1, d2, h, P, lb, G, gx, gy;
+    std::vector<int> mk;
+    explicit PatchWork(int RR) : d1(RR), d2(RR), h(RR * 4), P(RR * 6), lb(RR), G(RR * 6), gx(RR * 6), gy(RR * 6), mk(RR) {}
+};
+
+static void sobel_at(const float* p, int stride_row, float* sx, float* sy) {   // p points at the centre pixel
+    const float a = p[-stride_row - 1], b = p[-stride_row], c = p[-stride_row + 1];
+    const float d = p[-1], f = p[1];
+    const float g = p[stride_row - 1], h = p[stride_row], i = p[stride_row + 1];
+    *sx = (c - a) + 2.0f * (f - d) + (i - g);          // sobel_x = [[-1,0,1],[-2,0,2],[-1,0,1]]  (postprocessing_loss.py:19)
+    *sy = (a + 2.0f * b + c) - (g + 2.0f * h + i);     // sobel_y = [[1,2,1],[0,0,0],[-1,-2,-1]]   (:20)
+}
+
+int behm_global_loss(const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
+                     const float* bndry_depth, const float* gammas, int B, int H, int W, int R, int stride, float w, float lam,
+                     const float* cam7, int mode_local, float* terms, float* loss, float* grad, float* gimg, float* gbnd) {
+    const int Hp = (H - R) / stride + 1, Wp = (W - R) / stride + 1, RR = R * R, L = Hp * Wp, Ri = R - 2;
+    const size_t HW = (size_t)H * W;
+    const BeCam cam = make_cam(cam7);
+    const int nimg = mode_local ? 1 : 2;
+    const int np = mode_local ? 10 : 12;
+    const int pmode = mode_local ? BE_PARAMS_LOCALRAW10 : BE_PARAMS_RAW12;
+    auto ny = [&](int b, int m, int y, int x, int c) { return img_ny[((((size_t)b * nimg + m) * H + y) * W + x) * 3 + c]; };
+    auto gt = [&](int b, int m, int y, int x, int c) { return img_gt[((((size_t)b * nimg + m) * H + y) * W + x) * 3 + c]; };
+
+    // ---- pass 1: render + fold -> global image / boundary, mask count -------------------------------------------
+    std::vector<double> acc(mode_local ? 0 : (size_t)B * HW * 7, 0.0);
+    double msum = 0.0;
+    if (!mode_local) {
+        for (int b = 0; b < B; ++b)
+            for (int py = 0; py < Hp; ++py)
+                for (int px = 0; px < Wp; ++px) {
+                    BePatch P;
+                    be_patch_setup(raw + (((size_t)b * Hp + py) * Wp + px) * 12, pmode, cam, P);
+                    PatchWork wk(RR);
+                    float S[16] = {0};
+                    for (int q = 0; q < RR; ++q) {
+                        const int i = q / R, j = q % R;
+                        be_pixel_dists(P, be_axis(j, R), be_axis(i, R), w, &wk.d1[q], &wk.d2[q]);
+                        for (int m = 0; m < 2; ++m) {
+                            float u[3];
+                            wk.h[q * 4 + 2 * m] = be_h(wk.d1[q], P.inv_eta[2 * m]);
+                            wk.h[q * 4 + 2 * m + 1] = be_h(wk.d2[q], P.inv_eta[2 * m + 1]);
+                            be_wedges(wk.h[q * 4 + 2 * m], wk.h[q * 4 + 2 * m + 1], u);
+                            S[0] += u[0] * u[0]; S[1] += u[0] * u[1]; S[2] += u[0] * u[2];
+                            S[3] += u[1] * u[1]; S[4] += u[1] * u[2]; S[5] += u[2] * u[2];
+                            for (int wd = 0; wd < 3; ++wd)
+                                for (int c = 0; c < 3; ++c) S[6 + 3 * wd + c] += u[wd] * ny(b, m, py * stride + i, px * stride + j, c);
+                        }
+                    }
+                    double Minv[6];
+                    float C[9];
+                    be_solve_colors(S, lam, Minv, C);
+                    for (int q = 0; q < RR; ++q) {
+                        const int y = py * stride + q / R, x = px * stride + q % R;
+                        double* a = &acc[((size_t)b * HW + (size_t)y * W + x) * 7];
+                        for (int m = 0; m < 2; ++m) {
+                            float u[3];
+                            be_wedges(wk.h[q * 4 + 2 * m], wk.h[q * 4 + 2 * m + 1], u);
+                            for (int c = 0; c < 3; ++c) a[3 * m + c] += fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                        }
+                        a[6] += be_boundary(wk.d1[q], wk.d2[q]);
+                        const int mk = be_mask(wk.d1[q], wk.d2[q], false);
+                        if (mk != 0 && bndry_depth[(size_t)b * HW + (size_t)y * W + x] != 0.0f) msum += 1.0;
+                    }
+                }
+        for (int b = 0; b < B; ++b)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    const size_t p = (size_t)y * W + x;
+                    const float n = (float)(cover_1d(y, R, stride, Hp) * cover_1d(x, R, stride, Wp));
+                    for (int c = 0; c < 6; ++c) gimg[((size_t)b * 6 + c) * HW + p] = (float)acc[((size_t)b * HW + p) * 7 + c] / n;
+                    gbnd[(size_t)b * HW + p] = (float)acc[((size_t)b * HW + p) * 7 + 6] / n;
+                }
+    }
+
+    // ---- pass 2: per patch loss terms + backward ------------------------------------------------------------------
+    const double Np = (double)B * L;
+    double T[7] = {0, 0, 0, 0, 0, 0, 0};
+    float kc, kcc, kbc, ks, ksc, kbl, kd;
+    if (mode_local) {   // loss = colour + beta_loc * loc + beta_smth * smth   (local_training.py:47-52)
+        kc = (float)(gammas[0] / (RR * Np)); kcc = 0; kbc = 0; ks = (float)(gammas[2] / (Ri * Ri * Np)); ksc = 0;
+        kbl = (float)(gammas[1] / (RR * Np)); kd = 0;
+    } else {
+        kc = (float)(gammas[0] / (2.0 * RR * Np)); kcc = (float)(gammas[1] / (2.0 * RR * Np)); kbc = (float)(gammas[2] / (RR * Np));
+        ks = (float)(gammas[3] / (2.0 * Ri * Ri * Np)); ksc = (float)(gammas[4] / (2.0 * Ri * Ri * Np));
+        kbl = (float)(gammas[5] / (RR * Np)); kd = (float)(gammas[6] / msum);
+    }
+    for (int n = 0; n < B * L; ++n) {
+        const int b = n / L, py = (n / Wp) % Hp, px = n % Wp;
+        const int y0 = py * stride, x0 = px * stride;
+        BePatch P;
+        BePatchGrad PG;
+        be_patch_setup(raw + (size_t)n * np, pmode, cam, P);
+        be_patch_grad_setup(raw + (size_t)n * np, pmode, cam, P, PG);
+        PatchWork wk(RR);
+        float S[16] = {0};
+        for (int q = 0; q < RR; ++q) {
+            const int i = q / R, j = q % R;
+            be_pixel_dists(P, be_axis(j, R), be_axis(i, R), w, &wk.d1[q], &wk.d2[q]);
+            for (int m = 0; m < nimg; ++m) {
+                float u[3];
+                wk.h[q * 4 + 2 * m] = be_h(wk.d1[q], P.inv_eta[2 * m]);
+                wk.h[q * 4 + 2 * m + 1] = be_h(wk.d2[q], P.inv_eta[2 * m + 1]);
+                be_wedges(wk.h[q * 4 + 2 * m], wk.h[q * 4 + 2 * m + 1], u);
+                S[0] += u[0] * u[0]; S[1] += u[0] * u[1]; S[2] += u[0] * u[2];
+                S[3] += u[1] * u[1]; S[4] += u[1] * u[2]; S[5] += u[2] * u[2];
+                for (int wd = 0; wd < 3; ++wd)
+                    for (int c = 0; c < 3; ++c) S[6 + 3 * wd + c] += u[wd] * ny(b, m, y0 + i, x0 + j, c);
+            }
+        }
+        double Minv[6];
+        float C[9];
+        be_solve_colors(S, lam, Minv, C);
+        // render, direct gradient G = dL/dP
+        for (int q = 0; q < RR; ++q) {
+            const int y = y0 + q / R, x = x0 + q % R;
+            for (int m = 0; m < nimg; ++m) {
+                float u[3];
+                be_wedges(wk.h[q * 4 + 2 * m], wk.h[q * 4 + 2 * m + 1], u);
+                for (int c = 0; c < 3; ++c) {
+                    const float Pv = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                    wk.P[(3 * m + c) * RR + q] = Pv;
+                    const float e1 = Pv - gt(b, m, y, x, c);
+                    T[0] += (double)e1 * e1;
+                    float gval = 2.0f * kc * e1;
+                    if (!mode_local) {
+                        const float e2 = Pv - gimg[((size_t)b * 6 + 3 * m + c) * HW + (size_t)y * W + x];
+                        T[1] += (double)e2 * e2;
+                        gval += 2.0f * kcc * e2;
+                    }
+                    wk.G[(3 * m + c) * RR + q] = gval;
+                }
+            }
+            wk.lb[q] = be_boundary(wk.d1[q], wk.d2[q]);
+            wk.mk[q] = be_mask(wk.d1[q], wk.d2[q], false);
+        }
+        // smoothness: Sobel magnitude of the rendered patch vs targets, and its adjoint into G
+        std::fill(wk.gx.begin(), wk.gx.end(), 0.0f);
+        std::fill(wk.gy.begin(), wk.gy.end(), 0.0f);
+        for (int mc = 0; mc < 3 * nimg; ++mc)
+            for (int i = 1; i < R - 1; ++i)
+                for (int j = 1; j < R - 1; ++j) {
+                    float sx, sy;
+                    sobel_at(&wk.P[mc * RR + i * R + j], R, &sx, &sy);
+                    const float mag = sqrtf(sx * sx + sy * sy + 1e-8f);
+                    const int m = mc / 3, c = mc % 3;
+                    const float tg = deri[((((size_t)b * nimg + m) * (H - 2) + (y0 + i - 1)) * (W - 2) + (x0 + j - 1)) * 3 + c];
+                    const float e1 = mag - tg;
+                    T[3] += (double)e1 * e1;
+                    float gm = 2.0f * ks * e1;
+                    if (!mode_local) {
+                        float gsx, gsy;
+                        sobel_at(&gimg[((size_t)b * 6 + mc) * HW + (size_t)(y0 + i) * W + (x0 + j)], W, &gsx, &gsy);
+                        const float e2 = mag - sqrtf(gsx * gsx + gsy * gsy + 1e-8f);
+                        T[4] += (double)e2 * e2;
+                        gm += 2.0f * ksc * e2;
+                    }
+                    wk.gx[mc * RR + i * R + j] = gm * sx / mag;
+                    wk.gy[mc * RR + i * R + j] = gm * sy / mag;
+                }
+        static const float KX[3][3] = {{-1, 0, 1}, {-2, 0, 2}, {-1, 0, 1}}, KY[3][3] = {{1, 2, 1}, {0, 0, 0}, {-1, -2, -1}};
+        for (int mc = 0; mc < 3 * nimg; ++mc)
+            for (int i = 0; i < R; ++i)
+                for (int j = 0; j < R; ++j) {
+                    float s = 0.0f;   // adjoint: output (i',j') used input (i'+a-1, j'+b-1) with weight K[a][b]
+                    for (int a = 0; a < 3; ++a)
+                        for (int bb = 0; bb < 3; ++bb) {
+                            const int io = i - a + 1, jo = j - bb + 1;
+                            if (io < 1 || io > R - 2 || jo < 1 || jo > R - 2) continue;
+                            s += wk.gx[mc * RR + io * R + jo] * KX[a][bb] + wk.gy[mc * RR + io * R + jo] * KY[a][bb];
+                        }
+                    wk.G[mc * RR + i * R + j] += s;
+                }
+        // A^T G, second solve
+        float AtG[9] = {0}, V[9], Ssym[6];
+        for (int q = 0; q < RR; ++q)
+            for (int m = 0; m < nimg; ++m) {
+                float u[3];
+                be_wedges(wk.h[q * 4 + 2 * m], wk.h[q * 4 + 2 * m + 1], u);
+                for (int wd = 0; wd < 3; ++wd)
+                    for (int c = 0; c < 3; ++c) AtG[3 * wd + c] += u[wd] * wk.G[(3 * m + c) * RR + q];
+            }
+        be_backsolve(Minv, AtG, C, V, Ssym);
+        // per pixel backward
+        float geo[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, geta[4] = {0, 0, 0, 0}, gz[2] = {0, 0};
+        for (int q = 0; q < RR; ++q) {
+            const int i = q / R, j = q % R, y = y0 + i, x = x0 + j;
+            float gd1 = 0.0f, gd2 = 0.0f;
+            for (int m = 0; m < nimg; ++m) {
+                float u[3], gu[3], Gp[3], yv[3], gh1, gh2, a, bq;
+                const float h1 = wk.h[q * 4 + 2 * m], h2 = wk.h[q * 4 + 2 * m + 1];
+                be_wedges(h1, h2, u);
+                for (int c = 0; c < 3; ++c) { Gp[c] = wk.G[(3 * m + c) * RR + q]; yv[c] = ny(b, m, y, x, c); }
+                be_ridge_backward_pixel(Gp, yv, u, C, V, Ssym, gu);
+                be_wedges_backward(h1, h2, gu, &gh1, &gh2);
+                be_h_grad(wk.d1[q], P.inv_eta[2 * m], &a, &bq);
+                gd1 += gh1 * a; geta[2 * m] += gh1 * bq;
+                be_h_grad(wk.d2[q], P.inv_eta[2 * m + 1], &a, &bq);
+                gd2 += gh2 * a; geta[2 * m + 1] += gh2 * bq;
+            }
+            // boundary terms
+            const float lb = wk.lb[q];
+            float glb;
+            if (mode_local) {
+                const float bd = bndry_dist[(size_t)b * HW + (size_t)y * W + x];
+                T[5] += (double)(bd * lb) * (bd * lb);
+                glb = 2.0f * kbl * bd * bd * lb;
+            } else {
+                const float bd = log2f(bndry_dist[(size_t)b * HW + (size_t)y * W + x] + 1.0f);
+                const float e = lb - gbnd[(size_t)b * HW + (size_t)y * W + x];
+                T[2] += (double)e * e;
+                T[5] += (double)(bd * lb) * (bd * lb);
+                glb = 2.0f * kbc * e + 2.0f * kbl * bd * bd * lb;
+                // depth term
+                const float zg = bndry_depth[(size_t)b * HW + (size_t)y * W + x];
+                const int mk = wk.mk[q];
+                if (zg != 0.0f && mk != 0) {
+                    const float e2 = P.z[mk - 1] - zg;
+                    T[6] += (double)e2 * e2;
+                    gz[mk - 1] += 2.0f * kd * e2;
+                }
+            }
+            be_boundary_backward(wk.d1[q], wk.d2[q], lb, glb, &gd1, &gd2);
+            be_wedge_backward(P, 0, be_axis(j, R), be_axis(i, R), w, gd1, geo[0]);
+            be_wedge_backward(P, 1, be_axis(j, R), be_axis(i, R), w, gd2, geo[1]);
+        }
+        float* g = grad + (size_t)n * np;
+        for (int k = 0; k < 2; ++k) {
+            g[2 * k] = PG.xy_scale * geo[k][0];
+            g[2 * k + 1] = PG.xy_scale * geo[k][1];
+            g[4 + 2 * k] = PG.ang_scale * (geo[k][2] + geo[k][3]);
+            g[5 + 2 * k] = PG.ang_scale * geo[k][3];
+        }
+        if (mode_local) {
+            g[8] = geta[0] * PG.deta_dcoef[0];
+            g[9] = geta[1] * PG.deta_dcoef[1];
+        } else {
+            const float ge[4] = {geta[0] + gz[0] * PG.dz_deta[0], geta[1] + gz[1] * PG.dz_deta[2],
+                                 geta[2] + gz[0] * PG.dz_deta[1], geta[3] + gz[1] * PG.dz_deta[3]};
+            for (int k = 0; k < 4; ++k) g[8 + k] = ge[k] * PG.deta_dcoef[k];
+        }
+    }
+    if (mode_local) {
+        terms[0] = (float)(T[0] / (RR * Np)); terms[1] = (float)(T[5] / (RR * Np)); terms[2] = (float)(T[3] / (Ri * Ri * Np));
+        *loss = (float)(gammas[0] * terms[0] + gammas[1] * terms[1] + gammas[2] * terms[2]);
+    } else {
+        terms[0] = (float)(T[0] / (2.0 * RR * Np)); terms[1] = (float)(T[1] / (2.0 * RR * Np)); terms[2] = (float)(T[2] / (RR * Np));
+        terms[3] = (float)(T[3] / (2.0 * Ri * Ri * Np)); terms[4] = (float)(T[4] / (2.0 * Ri * Ri * Np));
+        terms[5] = (float)(T[5] / (RR * Np)); terms[6] = (float)(T[6] / msum);
+        double l = 0;
+        for (int k = 0; k < 7; ++k) l += (double)gammas[k] * terms[k];
+        *loss = (float)l;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -54,3 +54,36 @@ def render_fold(est, img_planar, g: O.Geometry, cam: O.Camera, rho_prime=10.39, 
                                 C.c_float(g.lam), _p(_cam7(cam, rho_prime)), C.c_int(int(densify == 'w')), *[_p(o) for o in outs])
     assert rc == 0
     return outs
+
+
+def global_loss(raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, gammas, g: O.Geometry, cam: O.Camera):
+    """fp32 host run of the loss kernel's algorithm: returns (loss, terms[7], grad [B,L,12], gimg [B,2,3,H,W], gbnd [B,H,W])."""
+    raw, img_ny, img_gt, bd, deri, zg = map(_f, (raw, img_ny, img_gt, bndry_dist, deri, bndry_depth))
+    B, H, W = raw.shape[0], g.H, g.W
+    gam = np.asarray(gammas, dtype=np.float32)
+    terms = np.zeros(7, np.float32)
+    loss = np.zeros(1, np.float32)
+    grad = np.zeros_like(raw)
+    gimg = np.zeros((B, 2, 3, H, W), np.float32)
+    gbnd = np.zeros((B, H, W), np.float32)
+    rc = lib().behm_global_loss(_p(raw), _p(img_ny), _p(img_gt), _p(bd), _p(deri), _p(zg), _p(gam), B, H, W, g.R, g.stride,
+                                C.c_float(g.w), C.c_float(g.lam), _p(_cam7(cam, 10.39)), 0, _p(terms), _p(loss), _p(grad),
+                                _p(gimg), _p(gbnd))
+    assert rc == 0
+    return float(loss[0]), terms, grad, gimg, gbnd
+
+
+def local_loss(est, img_ny, gt_img, bndry_dist, deri, betas, g: O.Geometry, cam: O.Camera):
+    """returns (loss, terms[3], grad [B,10])"""
+    est, img_ny, gt_img, bd, deri = map(_f, (est, img_ny, gt_img, bndry_dist, deri))
+    B, R = est.shape[0], g.R
+    gam = np.asarray([1.0, betas[0], betas[1], 0, 0, 0, 0], dtype=np.float32)
+    terms = np.zeros(7, np.float32)
+    loss = np.zeros(1, np.float32)
+    grad = np.zeros_like(est)
+    dummy = np.zeros(1, np.float32)
+    rc = lib().behm_global_loss(_p(est), _p(img_ny), _p(gt_img), _p(bd), _p(deri), _p(dummy), _p(gam), B, R, R, R, g.stride,
+                                C.c_float(g.w), C.c_float(g.lam), _p(_cam7(cam, 10.39)), 1, _p(terms), _p(loss), _p(grad),
+                                _p(dummy), _p(dummy))
+    assert rc == 0
+    return float(loss[0]), terms[:3], grad

@@ -35,3 +35,45 @@ def test_pass_b(gname, densify, kind, tol):
         e = relmax(o, r.numpy())
         lim = tol if name not in ('sharp',) else max(tol, 2e-3)   # eta=1e-4 render: edge pixels amplify 1-ulp distance noise
         assert e < lim, (name, e)
+
+
+def _grad_err(got, ref):
+    """max-norm and rel-L2 error of a gradient tensor"""
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(got - ref).max() / np.abs(ref).max()), float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+
+
+GAMMA_SETS = [[1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 1e-4], [0.1, 0.05, 0.02, 0.002, 0.002, 1e-4, 0.5]] + \
+             [[1.0 if k == j else 0.0 for k in range(7)] for j in range(7)]
+
+
+@pytest.mark.parametrize('gname', list(GEOMS))
+@pytest.mark.parametrize('gammas', GAMMA_SETS)
+def test_global_loss_forward_backward(gname, gammas):
+    """Analytic backward of the kernels (be_math.cuh) vs autograd through the fp64 oracle, term by term."""
+    from common import gloss_inputs
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs(gname, 'normal', F32)
+    r64 = raw.to(F64).requires_grad_(True)
+    loss, terms, aux = O.global_loss(r64, img_ny.to(F64), img_gt.to(F64), bd.to(F64), deri.to(F64), zgt.to(F64), gammas, g, CAM,
+                                     return_terms=True)
+    (gref,) = torch.autograd.grad(loss, r64)
+    l, t, grad, gimg, gbnd = hostmath.global_loss(raw, img_ny, img_gt, bd, deri, zgt, gammas, g, CAM)
+    assert abs(l - loss.item()) <= 2e-6 * abs(loss.item())
+    np.testing.assert_allclose(t, terms.detach().numpy(), rtol=5e-6)
+    assert relmax(gimg, aux['gimg'].numpy()) < 1e-5 and relmax(gbnd, aux['gbnd'].numpy()[:, 0]) < 1e-5
+    emax, el2 = _grad_err(grad, gref.numpy())
+    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)   # fp32 sums of <=882 terms; the reference's own fp32 grads: rel-L2 1e-4
+
+
+@pytest.mark.parametrize('betas', [(0.001, 0.0005), (1.0, 0.0), (0.0, 1.0)])
+def test_local_loss_forward_backward(betas):
+    g = geom(147)
+    est, ny, gt, bd, deri = synth.local_batch(8, 21, seed=41)
+    e64 = est.to(F64).requires_grad_(True)
+    loss, terms, _ = O.local_loss(e64, ny.to(F64), gt.to(F64), bd.to(F64), deri.to(F64), betas, g, return_terms=True)
+    (gref,) = torch.autograd.grad(loss, e64)
+    l, t, grad = hostmath.local_loss(est, ny, gt, bd, deri, betas, g, CAM)
+    assert abs(l - loss.item()) <= 2e-6 * abs(loss.item())
+    np.testing.assert_allclose(t, terms.detach().numpy(), rtol=5e-6)
+    emax, el2 = _grad_err(grad, gref.numpy())
+    assert emax < 2e-5 and el2 < 2e-5, (emax, el2)
