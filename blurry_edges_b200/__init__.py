@@ -6,5 +6,6 @@ any of its classes on a machine without the built library or without a CUDA devi
 from . import _lib
 from ._lib import BlurryEdgesError, Context, make_config
 from .fused import PostProcessFused
+from .losses import GlobalLossFused, LocalLossFused
 
-__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', '_lib']
+__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', '_lib']

@@ -49,6 +49,9 @@ _SIGS = {
     'be_colors_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, _P, _P]),
     'be_render_fold_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P, _P]),
+    'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
+    'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
     'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P]),
 }
@@ -215,6 +218,41 @@ class Context:
         if want_thresholded:
             out.append(torch.empty(B, H, W, **kw))
         return out
+
+    # ---- training entry points -----------------------------------------------------------
+    def global_loss_stage1(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, want_maps=True):
+        """-> (global_image [B,2,3,H,W] | None, global_bndry [B,1,H,W] | None, mask_count int64[1])"""
+        B, H, W, kw = raw.shape[0], self.cfg.H, self.cfg.W, dict(device=self.device, dtype=torch.float32)
+        gimg = torch.empty(B, 2, 3, H, W, **kw) if want_maps else None
+        gbnd = torch.empty(B, 1, H, W, **kw) if want_maps else None
+        cnt = torch.zeros(1, device=self.device, dtype=torch.int64)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_global_loss_stage1(self.h, _ptr(raw), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri),
+                                                 _ptr(bndry_depth), B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()),
+                                                 _stream(self.device)))
+        return gimg, gbnd, cnt
+
+    def global_loss_stage2(self, B, gammas, global_patches, mask_count, want_grad=True):
+        """-> (terms [7], loss [1], grad [B,L,12] | None)"""
+        kw = dict(device=self.device, dtype=torch.float32)
+        terms, loss = torch.empty(7, **kw), torch.empty(1, **kw)
+        grad = torch.empty(B, self.L, 12, **kw) if want_grad else None
+        gam = (C.c_double * 7)(*[float(x) for x in gammas])
+        with torch.cuda.device(self.device):
+            check(self.lib.be_global_loss_stage2(self.h, B, gam, int(global_patches), C.c_void_p(mask_count.data_ptr()),
+                                                 _ptr(terms), _ptr(loss), _ptr(grad), _stream(self.device)))
+        return terms, loss, grad
+
+    def local_loss(self, est, img_ny, img_gt, bndry_dist, deri, beta_bndry_loc, beta_smthns, want_grad=True):
+        """-> (terms [3], loss [1], grad [B,10] | None)"""
+        B, kw = est.shape[0], dict(device=self.device, dtype=torch.float32)
+        terms, loss = torch.empty(3, **kw), torch.empty(1, **kw)
+        grad = torch.empty(B, 10, **kw) if want_grad else None
+        with torch.cuda.device(self.device):
+            check(self.lib.be_local_loss(self.h, _ptr(est), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri), B,
+                                         float(beta_bndry_loc), float(beta_smthns), _ptr(terms), _ptr(loss), _ptr(grad),
+                                         _stream(self.device)))
+        return terms, loss, grad
 
     # ---- host-buffer entry point (numpy / pinned host tensors in, numpy out) ------------
     def host_render_fold(self, est, img, layout: BeImageLayout, densify_w=False, param_mode=PARAMS_RESTORED12, out=None):

@@ -50,6 +50,11 @@ struct be_ctx {
     float* st_out;
     size_t st_bytes;
     cudaStream_t st_stream;
+    // training workspace (lazily allocated by the loss entry points)
+    float* gtable;      // [max_batch*L][BE_GREC]
+    float* T;           // [max_batch][H][W][BE_TW]
+    float* partials;    // [max_batch*Hp*runs][8]
+    size_t train_bytes;
     // optional per-kernel timing of the last be_render_fold_fwd call (be_ctx_set_timing)
     int timing;
     cudaEvent_t ev[5];
@@ -172,13 +177,14 @@ int be_ctx_destroy(be_ctx* c) {
     if (!c) return 0;
     cudaFree(c->table); cudaFree(c->acc);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
+    cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials);
     if (c->st_stream) cudaStreamDestroy(c->st_stream);
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     return 0;
 }
 
-int64_t be_ctx_workspace_bytes(const be_ctx* c) { return c ? (int64_t)(c->table_bytes + c->acc_bytes + c->st_bytes) : 0; }
+int64_t be_ctx_workspace_bytes(const be_ctx* c) { return c ? (int64_t)(c->table_bytes + c->acc_bytes + c->st_bytes + c->train_bytes) : 0; }
 
 int be_ctx_constants(const be_ctx* c, double* out8) {
     BE_REQUIRE(c && out8, "null argument");
@@ -230,7 +236,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     if (M == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int L = c->g.Hp * c->g.Wp;
-    be_launch_setup(dev_est, param_mode, M * L, c->cam, c->table, st);
+    be_launch_setup(dev_est, param_mode, M * L, c->cam, c->table, nullptr, st);
     BeRunArgs a;
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
@@ -257,7 +263,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     if (tm) cudaEventRecord(c->ev[0], st);
     BE_CUDA(cudaMemsetAsync(c->acc, 0, (size_t)B * g.H * g.W * BE_ACC * sizeof(float), st));
     if (tm) cudaEventRecord(c->ev[1], st);
-    be_launch_setup(dev_est, param_mode, B * L, c->cam, c->table, st);
+    be_launch_setup(dev_est, param_mode, B * L, c->cam, c->table, nullptr, st);
     if (tm) cudaEventRecord(c->ev[2], st);
     BeRunArgs a;
     memset(&a, 0, sizeof(a));
@@ -269,6 +275,115 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
     be_launch_normalise(c->acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
     if (tm) cudaEventRecord(c->ev[4], st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// training entry points
+// ---------------------------------------------------------------------------------------------------
+static int ensure_train_ws(be_ctx* c) {
+    if (c->gtable) return 0;
+    const BeGeom& g = c->g;
+    const size_t mb = (size_t)c->cfg.max_batch, L = (size_t)g.Hp * g.Wp;
+    int G, runs;
+    pick_runs(g, &G, &runs);
+    const size_t b1 = mb * L * BE_GREC * sizeof(float), b2 = mb * g.H * g.W * BE_TW * sizeof(float);
+    const size_t b3 = mb * g.Hp * runs * 8 * sizeof(float);
+    BE_CUDA(cudaMalloc(&c->gtable, b1));
+    BE_CUDA(cudaMalloc(&c->T, b2));
+    BE_CUDA(cudaMalloc(&c->partials, b3));
+    c->train_bytes = b1 + b2 + b3;
+    return 0;
+}
+
+int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                          const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                          float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream) {
+    if (check_ctx(c)) return 1;
+    if (B == 0) return 0;
+    BE_REQUIRE(dev_raw && dev_img_ny && dev_img_gt && dev_bndry_dist && dev_deri && dev_bndry_depth && dev_mask_count, "null pointer");
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
+    if (ensure_train_ws(c)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const BeGeom& g = c->g;
+    const int L = g.Hp * g.Wp;
+    const size_t HW = (size_t)g.H * g.W;
+    BE_CUDA(cudaMemsetAsync(c->acc, 0, (size_t)B * HW * 8 * sizeof(float), st));
+    BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), st));
+    be_launch_setup(dev_raw, BE_PARAMS_RAW12, B * L, c->cam, c->table, c->gtable, st);
+    BeRunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table; a.acc = c->acc;
+    a.img.p = dev_img_ny; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
+    a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
+    a.g = g; a.cam = c->cam; a.NB = B;
+    pick_runs(g, &a.G, &a.runs_per_row);
+    be_launch_run(BE_RUN_TRAINFWD, a, st);
+    be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
+    be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                          float* dev_terms, float* dev_loss, float* dev_grad, void* stream) {
+    if (check_ctx(c)) return 1;
+    if (B == 0) return 0;
+    BE_REQUIRE(gammas7 && dev_mask_count && dev_terms && dev_loss, "null pointer");
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
+    BE_REQUIRE(c->gtable, "be_global_loss_stage1 must run first");
+    BE_REQUIRE(global_patches > 0, "global_patches must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const BeGeom& g = c->g;
+    const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)global_patches;
+    BeLossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table; a.gtable = c->gtable; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
+    a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
+    a.g = g; a.NB = B;
+    pick_runs(g, &a.G, &a.runs_per_row);
+    BeLossScale sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.nterms = 7;
+    const double norm[7] = {2 * RR * Np, 2 * RR * Np, RR * Np, 2 * Ri2 * Np, 2 * Ri2 * Np, RR * Np, 1.0};
+    for (int t = 0; t < 7; ++t) { sc.src[t] = t; sc.scale[t] = 1.0 / norm[t]; sc.gamma[t] = (float)gammas7[t]; sc.masked[t] = (t == 6); }
+    a.kc = (float)(gammas7[0] / norm[0]); a.kcc = (float)(gammas7[1] / norm[1]); a.kbc = (float)(gammas7[2] / norm[2]);
+    a.ks = (float)(gammas7[3] / norm[3]); a.ksc = (float)(gammas7[4] / norm[4]); a.kbl = (float)(gammas7[5] / norm[5]);
+    a.gamma_d = (float)gammas7[6];
+    be_launch_loss(false, a, st);
+    be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
+                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, float* dev_terms, float* dev_loss,
+                  float* dev_grad, void* stream) {
+    if (check_ctx(c)) return 1;
+    if (B == 0) return 0;
+    BE_REQUIRE(dev_est && dev_img_ny && dev_img_gt && dev_bndry_dist && dev_deri && dev_terms && dev_loss, "null pointer");
+    const BeGeom& g = c->g;
+    BE_REQUIRE(g.H == g.R && g.W == g.R, "be_local_loss needs a context whose image is one %dx%d patch (got %dx%d)", g.R, g.R, g.H, g.W);
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
+    if (ensure_train_ws(c)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    be_launch_setup(dev_est, BE_PARAMS_LOCALRAW10, B, c->cam, c->table, c->gtable, st);
+    const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)B;
+    BeLossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table; a.gtable = c->gtable; a.grad = dev_grad; a.partials = c->partials;
+    a.l_ny = dev_img_ny; a.l_gt = dev_img_gt; a.l_bd = dev_bndry_dist; a.l_deri = dev_deri;
+    a.g = g; a.NB = B; a.G = 1; a.runs_per_row = 1;
+    BeLossScale sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.nterms = 3;                                        // loss = colour + beta_loc * loc + beta_smth * smth (local_training.py:47-52)
+    sc.src[0] = 0; sc.src[1] = 5; sc.src[2] = 3;
+    sc.scale[0] = 1.0 / (RR * Np); sc.scale[1] = 1.0 / (RR * Np); sc.scale[2] = 1.0 / (Ri2 * Np);
+    sc.gamma[0] = 1.0f; sc.gamma[1] = (float)beta_bndry_loc; sc.gamma[2] = (float)beta_smthns;
+    a.kc = (float)sc.scale[0]; a.kbl = (float)(beta_bndry_loc * sc.scale[1]); a.ks = (float)(beta_smthns * sc.scale[2]);
+    be_launch_loss(true, a, st);
+    be_launch_loss_reduce(c->partials, B, sc, nullptr, dev_terms, dev_loss, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,8 +10,10 @@ constexpr int BE_THREADS = 224;       // 7 warps
 constexpr int BE_WARPS = BE_THREADS / 32;
 constexpr int BE_REC = 32;            // floats per patch-table record (128 B)
 constexpr int BE_ACC = 16;            // floats per pixel of the fold accumulator (15 used)
+constexpr int BE_GREC = 12;           // floats per patch of the backward chain-rule record
+constexpr int BE_TW = 36;             // floats per pixel of the packed training-target record (be_train.cu)
 
-enum BeRunMode { BE_RUN_COLORS = 0, BE_RUN_INFER = 1 };
+enum BeRunMode { BE_RUN_COLORS = 0, BE_RUN_INFER = 1, BE_RUN_TRAINFWD = 2 };
 
 struct BeGeom {
     int R, stride, H, W, Hp, Wp;
@@ -28,6 +30,8 @@ struct BeRunArgs {
     BeImg img;
     float* acc;                       // [NB][H][W][BE_ACC] fold accumulator (INFER)
     float* colors;                    // [NB][3][3][Hp][Wp]               (COLORS)
+    const float* zgt;                 // [NB][H][W] ground-truth boundary depth (TRAINFWD)
+    unsigned long long* mask_count;   // sum over the batch of [z_gt != 0 and mask != 0] (TRAINFWD)
     BeGeom g;
     BeCam cam;
     int NB;                           // pairs (INFER) or single images (COLORS)
@@ -35,8 +39,35 @@ struct BeRunArgs {
     int densify_w;
 };
 
-// launchers (be_kernels.cu); all asynchronous on `st`
-void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, cudaStream_t st);
+struct BeLossArgs {
+    const float* table;               // [N][BE_REC]
+    const float* gtable;              // [N][BE_GREC]
+    const float* T;                   // [NB][H][W][BE_TW] packed targets (global loss)
+    const float *l_ny, *l_gt, *l_bd, *l_deri;   // local loss: [NB,R,R,3], [NB,R,R,3], [NB,R,R], [NB,R-2,R-2,3]
+    float* grad;                      // [N][12|10] or nullptr
+    float* partials;                  // [grid][8]
+    const unsigned long long* mask_count;
+    BeGeom g;
+    int NB, G, runs_per_row;
+    float kc, kcc, kbc, ks, ksc, kbl, gamma_d;   // gamma_k / (normaliser_k * N_patches); depth: gamma_d / mask_count
+};
+
+struct BeLossScale {                  // partial sums -> reported terms
+    int nterms;
+    int src[7];
+    double scale[7];
+    float gamma[7];
+    int masked[7];
+};
+
+// launchers (be_kernels.cu / be_train.cu); all asynchronous on `st`
+void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, float* gtable, cudaStream_t st);
+void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st);
+void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
+                          const float* bndry_depth, float* T, cudaStream_t st);
+void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st);
+void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
+                           float* loss, cudaStream_t st);
 void be_launch_run(int mode, const BeRunArgs& a, cudaStream_t st);
 void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st);

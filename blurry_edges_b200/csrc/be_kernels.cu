@@ -28,7 +28,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // per-patch records
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) be_setup_kernel(const float* __restrict__ est, int param_mode, int npatch,
-                                                       BeCam cam, float* __restrict__ table) {
+                                                       BeCam cam, float* __restrict__ table, float* __restrict__ gtable) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= npatch) return;
     const int np = (param_mode == BE_PARAMS_LOCAL10 || param_mode == BE_PARAMS_LOCALRAW10) ? 10 : 12;
@@ -45,6 +45,14 @@ __global__ void __launch_bounds__(128) be_setup_kernel(const float* __restrict__
     rec[5] = make_float4(P.eta[0], P.eta[1], P.eta[2], P.eta[3]);
     rec[6] = make_float4(0.f, 0.f, 0.f, 0.f);
     rec[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gtable) {   // chain-rule scalars of the backward pass
+        BePatchGrad G;
+        be_patch_grad_setup(p, param_mode, cam, P, G);
+        float4* gr = reinterpret_cast<float4*>(gtable + (size_t)n * BE_GREC);
+        gr[0] = make_float4(G.deta_dcoef[0], G.deta_dcoef[1], G.deta_dcoef[2], G.deta_dcoef[3]);
+        gr[1] = make_float4(G.dz_deta[0], G.dz_deta[1], G.dz_deta[2], G.dz_deta[3]);
+        gr[2] = make_float4(G.xy_scale, G.ang_scale, 0.f, 0.f);
+    }
 }
 
 __device__ __forceinline__ void load_record(const float* rec, BePatch& P) {
@@ -86,8 +94,11 @@ __device__ __forceinline__ float ld_img(const BeImg& im, int b, int m, int c, in
 template <int MODE>
 __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
     constexpr bool INFER = (MODE == BE_RUN_INFER);
-    constexpr int NIMG = INFER ? 2 : 1;          // images whose pixels enter the normal equations
-    constexpr int NACC = INFER ? 15 : 1;
+    constexpr bool TRAIN = (MODE == BE_RUN_TRAINFWD);   // global-loss forward: 2 renders + boundary -> 7 folded planes
+    constexpr bool FOLD = INFER || TRAIN;
+    constexpr int NIMG = FOLD ? 2 : 1;           // images whose pixels enter the normal equations
+    constexpr int NACC = INFER ? 15 : (TRAIN ? 7 : 1);
+    constexpr int ACCW = INFER ? BE_ACC : 8;     // floats per pixel of the fold accumulator
 
     __shared__ __align__(16) float s_rec[2][BE_REC];
     __shared__ float s_axis[BE_MAX_R + 3];
@@ -117,6 +128,8 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
     float Y[2];
     float pix[2][3 * NIMG];
     float acc[2][NACC];
+    float zg[2] = {0.0f, 0.0f};                  // TRAIN: ground-truth boundary depth at the slot's pixel
+    unsigned mcount = 0;                         // TRAIN: #[z_gt != 0 and mask != 0]   (global_training.py:125-127)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int slot = tid + s * BE_THREADS;
@@ -135,6 +148,7 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
         for (int m = 0; m < NIMG; ++m)
 #pragma unroll
             for (int c = 0; c < 3; ++c) pix[s][3 * m + c] = ld_img(a.img, b, m, c, y0 + si[s], x);
+        if (TRAIN) zg[s] = __ldg(a.zgt + ((size_t)b * g.H + y0 + si[s]) * g.W + x);
     }
 
     const float inv_sharp = 1.0f / (BE_SQRT2_F * BE_ETA_SHARP);
@@ -175,6 +189,7 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
                     const int mk = be_mask(d1[s], d2[s], a.densify_w != 0);
                     sums[15] += (mk == 1) ? 1.0f : ((mk == 2) ? 1024.0f : 0.0f);   // two exact counters in one float
                 }
+                if (TRAIN) mcount += (be_mask(d1[s], d2[s], false) != 0 && zg[s] != 0.0f) ? 1u : 0u;
             }
         }
         const float tot = warp_reduce16(sums, lane);
@@ -194,18 +209,25 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
             double Minv[6];
             float C[9];
             be_solve_colors(S, g.lam, Minv, C);
+            if (FOLD && lane == 0) {   // static indices only: a lane-indexed register array would live in local memory
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s_col[q] = C[q];
+            }
             if (INFER) {
-                if (lane < 9) s_col[lane] = C[lane];
                 if (lane == 9 || lane == 10) {
                     const int cnt = (int)S[15];
                     const int have = (lane == 9) ? (cnt & 1023) : (cnt >> 10);
                     const float sg = have > 0 ? be_refocus_sigma(a.cam, (lane == 9) ? P.z[0] : P.z[1]) : BE_ETA_SHARP;   // blurry_edges_test.py:66-72
                     s_col[lane] = 1.0f / (BE_SQRT2_F * sg);
                 }
-            } else if (lane < 9) {
+            }
+            if (!FOLD && lane == 0) {
                 // colours [NB][3(channel)][3(wedge)][Hp][Wp]  (blurry_edges_test.py:27 permute)
-                const int wd = lane / 3, c = lane % 3;
-                a.colors[(((size_t)b * 3 + c) * 3 + wd) * g.Hp * g.Wp + (size_t)py * g.Wp + px0 + k] = C[lane];
+                float* dst = a.colors + (size_t)b * 9 * g.Hp * g.Wp + (size_t)py * g.Wp + px0 + k;
+#pragma unroll
+                for (int wd = 0; wd < 3; ++wd)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) dst[(size_t)(c * 3 + wd) * g.Hp * g.Wp] = C[3 * wd + c];
             }
             if (lane < 8 && k + 1 < n) reinterpret_cast<float4*>(s_rec[cur ^ 1])[lane] = nxt;
         }
@@ -242,19 +264,43 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
             }
         }
 
+        if (TRAIN) {
+            float C[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) C[q] = s_col[q];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (valid[s]) {
+                    float u[3];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        be_wedges(h[s][2 * m], h[s][2 * m + 1], u);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            acc[s][3 * m + c] += fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                    }
+                    acc[s][6] += be_boundary(d1[s], d2[s]);
+                }
+            }
+        }
+
         // ---------------- slide the window by one patch ----------------
         const bool last = (k + 1 == n);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (!valid[s]) continue;
             const int jn = j[s] - g.stride;
-            if (INFER && (last || jn < 0)) {
+            if (FOLD && (last || jn < 0)) {
                 const int x = (px0 + k) * g.stride + j[s];
-                float4* dst = reinterpret_cast<float4*>(a.acc + (((size_t)b * g.H + y0 + si[s]) * g.W + x) * BE_ACC);
+                float4* dst = reinterpret_cast<float4*>(a.acc + (((size_t)b * g.H + y0 + si[s]) * g.W + x) * ACCW);
                 atomicAdd(dst + 0, make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]));
-                atomicAdd(dst + 1, make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]));
-                atomicAdd(dst + 2, make_float4(acc[s][8], acc[s][9], acc[s][10], acc[s][11]));
-                atomicAdd(dst + 3, make_float4(acc[s][12], acc[s][13], acc[s][14], 0.0f));
+                if (INFER) {
+                    atomicAdd(dst + 1, make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7 % NACC]));
+                    atomicAdd(dst + 2, make_float4(acc[s][8 % NACC], acc[s][9 % NACC], acc[s][10 % NACC], acc[s][11 % NACC]));
+                    atomicAdd(dst + 3, make_float4(acc[s][12 % NACC], acc[s][13 % NACC], acc[s][14 % NACC], 0.0f));
+                } else {
+                    atomicAdd(dst + 1, make_float4(acc[s][4 % NACC], acc[s][5 % NACC], acc[s][6 % NACC], 0.0f));
+                }
 #pragma unroll
                 for (int q = 0; q < NACC; ++q) acc[s][q] = 0.0f;
             }
@@ -266,11 +312,16 @@ __global__ void __maxnreg__(96) be_run_kernel(const BeRunArgs a) {
                     for (int m = 0; m < NIMG; ++m)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) pix[s][3 * m + c] = ld_img(a.img, b, m, c, y0 + si[s], x);
+                    if (TRAIN) zg[s] = __ldg(a.zgt + ((size_t)b * g.H + y0 + si[s]) * g.W + x);
                 } else {
                     j[s] = jn;
                 }
             }
         }
+    }
+    if (TRAIN) {
+        mcount = __reduce_add_sync(FULL, mcount);
+        if (lane == 0 && mcount) atomicAdd(a.mask_count, (unsigned long long)mcount);
     }
 }
 
@@ -338,14 +389,15 @@ __global__ void __launch_bounds__(256) be_cover_count_kernel(BeGeom g, float* __
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
-void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, cudaStream_t st) {
-    be_setup_kernel<<<(npatch + 127) / 128, 128, 0, st>>>(est, param_mode, npatch, cam, table);
+void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, float* gtable, cudaStream_t st) {
+    be_setup_kernel<<<(npatch + 127) / 128, 128, 0, st>>>(est, param_mode, npatch, cam, table, gtable);
     ++g_be_launches;
 }
 
 void be_launch_run(int mode, const BeRunArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
     if (mode == BE_RUN_INFER) be_run_kernel<BE_RUN_INFER><<<grid, BE_THREADS, 0, st>>>(a);
+    else if (mode == BE_RUN_TRAINFWD) be_run_kernel<BE_RUN_TRAINFWD><<<grid, BE_THREADS, 0, st>>>(a);
     else be_run_kernel<BE_RUN_COLORS><<<grid, BE_THREADS, 0, st>>>(a);
     ++g_be_launches;
 }

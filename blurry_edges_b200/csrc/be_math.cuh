@@ -240,6 +240,7 @@ BE_HD void be_solve_colors(const float* S, float lam, double* Minv, float* C) {
     const double idet = 1.0 / (a * A00 + b * A01 + c * A02);
     Minv[0] = A00 * idet; Minv[1] = A01 * idet; Minv[2] = A02 * idet;
     Minv[3] = A11 * idet; Minv[4] = A12 * idet; Minv[5] = A22 * idet;
+#pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const double b0 = S[6 + ch], b1 = S[9 + ch], b2 = S[12 + ch];
         C[0 + ch] = (float)(Minv[0] * b0 + Minv[1] * b1 + Minv[2] * b2);
@@ -309,37 +310,35 @@ BE_HD void be_patch_grad_setup(const float* p, int mode, const BeCam& cam, const
 BE_HD void be_wedge_backward(const BePatch& P, int k, float X, float Y, float w, float g, float* acc) {
     const float dx = X - P.vx[k], dy = Y - P.vy[k];
     const float f = P.flip[k];
-    float d[2], a[2], D[2];
-    for (int e = 0; e < 2; ++e) {
-        const float sn = P.sn[2 * k + e], cs = P.cs[2 * k + e];
-        d[e] = fmaf(cs, dy, -sn * dx);
-        a[e] = fmaf(cs, dx, sn * dy);
-        const float aw = a[e] * w;
-        const float cap = be_sqrt(fmaf(d[e], d[e], aw * aw));
-        D[e] = (a[e] < 0.0f) ? ((d[e] < 0.0f) ? -cap : cap) : d[e];
-    }
-    const bool in = (k == 0) ? ((f * D[0] > 0.0f) && (f * D[1] < 0.0f)) : ((f * D[0] >= 0.0f) && (f * D[1] <= 0.0f));
+    const float snA = P.sn[2 * k], csA = P.cs[2 * k], snB = P.sn[2 * k + 1], csB = P.cs[2 * k + 1];
+    const float dA = fmaf(csA, dy, -snA * dx), aA = fmaf(csA, dx, snA * dy);
+    const float dB = fmaf(csB, dy, -snB * dx), aB = fmaf(csB, dx, snB * dy);
+    const float capA = be_sqrt(fmaf(dA, dA, (aA * w) * (aA * w))), capB = be_sqrt(fmaf(dB, dB, (aB * w) * (aB * w)));
+    const float DA = (aA < 0.0f) ? ((dA < 0.0f) ? -capA : capA) : dA;
+    const float DB = (aB < 0.0f) ? ((dB < 0.0f) ? -capB : capB) : dB;
+    const bool in = (k == 0) ? ((f * DA > 0.0f) && (f * DB < 0.0f)) : ((f * DA >= 0.0f) && (f * DB <= 0.0f));
     const float sg = g * (in ? f : -f);
-    const float absA = fabsf(D[0]), absB = fabsf(D[1]);
+    const float absA = fabsf(DA), absB = fabsf(DB);
     const float wA = (absA < absB) ? 1.0f : ((absA == absB) ? 0.5f : 0.0f);
-    for (int e = 0; e < 2; ++e) {
-        const float we = (e == 0) ? wA : 1.0f - wA;
-        if (we == 0.0f) continue;
-        const float absD = (e == 0) ? absA : absB;
-        float gd, ga;
-        if (a[e] < 0.0f) {
-            const float ir = (absD > 0.0f) ? 1.0f / absD : 0.0f;          // |D| = r on this branch
-            gd = sg * we * d[e] * ir;
-            ga = sg * we * (w * w) * a[e] * ir;
-        } else {
-            gd = sg * we * ((d[e] > 0.0f) ? 1.0f : ((d[e] < 0.0f) ? -1.0f : 0.0f));
-            ga = 0.0f;
-        }
-        const float sn = P.sn[2 * k + e], cs = P.cs[2 * k + e];
-        acc[0] += gd * sn - ga * cs;
-        acc[1] += -gd * cs - ga * sn;
-        acc[2 + e] += -gd * a[e] + ga * d[e];
+    const float wB = 1.0f - wA;
+    // edge A
+    float gdA, gaA, gdB, gaB;
+    if (aA < 0.0f) {
+        const float ir = (absA > 0.0f) ? 1.0f / absA : 0.0f;             // |D| = r on the cap branch
+        gdA = sg * wA * dA * ir; gaA = sg * wA * (w * w) * aA * ir;
+    } else {
+        gdA = sg * wA * ((dA > 0.0f) ? 1.0f : ((dA < 0.0f) ? -1.0f : 0.0f)); gaA = 0.0f;
     }
+    if (aB < 0.0f) {
+        const float ir = (absB > 0.0f) ? 1.0f / absB : 0.0f;
+        gdB = sg * wB * dB * ir; gaB = sg * wB * (w * w) * aB * ir;
+    } else {
+        gdB = sg * wB * ((dB > 0.0f) ? 1.0f : ((dB < 0.0f) ? -1.0f : 0.0f)); gaB = 0.0f;
+    }
+    acc[0] += (gdA * snA - gaA * csA) + (gdB * snB - gaB * csB);
+    acc[1] += (-gdA * csA - gaA * snA) + (-gdB * csB - gaB * snB);
+    acc[2] += -gdA * aA + gaA * dA;
+    acc[3] += -gdB * aB + gaB * dB;
 }
 
 // boundary map backward (blurry_edges_test.py:59-61): glb = dL/d lb -> adds to gd1, gd2
@@ -360,27 +359,31 @@ BE_HD void be_wedges_backward(float h1, float h2, const float* gu, float* gh1, f
 // Second solve of the ridge backward: V = Minv (A^T G), Ssym = V C^T + C V^T (packed 00,01,02,11,12,22).
 // AtG[3*w + c], C[3*w + c], V[3*w + c].
 BE_HD void be_backsolve(const double* Minv, const float* AtG, const float* C, float* V, float* Ssym) {
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
         const double b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
         V[0 + c] = (float)(Minv[0] * b0 + Minv[1] * b1 + Minv[2] * b2);
         V[3 + c] = (float)(Minv[1] * b0 + Minv[3] * b1 + Minv[4] * b2);
         V[6 + c] = (float)(Minv[2] * b0 + Minv[4] * b1 + Minv[5] * b2);
     }
-    int q = 0;
-    for (int i = 0; i < 3; ++i)
-        for (int j = i; j < 3; ++j) {
-            float s = 0.0f;
-            for (int c = 0; c < 3; ++c) s += V[3 * i + c] * C[3 * j + c] + C[3 * i + c] * V[3 * j + c];
-            Ssym[q++] = s;
-        }
+    const int pi[6] = {0, 0, 0, 1, 1, 2}, pj[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s += V[3 * pi[q] + c] * C[3 * pj[q] + c] + C[3 * pi[q] + c] * V[3 * pj[q] + c];
+        Ssym[q] = s;
+    }
 }
 
 // dL/du for one pixel of one image: G (3 channels) = dL/dP, y (3) = regression pixel, u (3) = wedges.
 BE_HD void be_ridge_backward_pixel(const float* G, const float* y, const float* u, const float* C, const float* V,
                                    const float* Ssym, float* gu) {
     const float S[9] = {Ssym[0], Ssym[1], Ssym[2], Ssym[1], Ssym[3], Ssym[4], Ssym[2], Ssym[4], Ssym[5]};
+#pragma unroll
     for (int w = 0; w < 3; ++w) {
         float s = 0.0f;
+#pragma unroll
         for (int c = 0; c < 3; ++c) s += G[c] * C[3 * w + c] + y[c] * V[3 * w + c];
         gu[w] = s - (S[3 * w] * u[0] + S[3 * w + 1] * u[1] + S[3 * w + 2] * u[2]);
     }

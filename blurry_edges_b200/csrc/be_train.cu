@@ -1,0 +1,603 @@
+// sm_100a kernels of the TRAINING side: global-stage loss (global_training.py:62-157) and local-stage loss
+// (local_training.py:32-52), forward + analytic backward, plus the small kernels between the two passes.
+//
+//   be_run_kernel<TRAINFWD>   (be_kernels.cu) renders both images + boundary and folds them -> accumulator [B,H,W,8],
+//                             counts the depth-term mask.
+//   be_train_normalise_kernel accumulator -> global image / boundary (detached targets, :154-155), written into the
+//                             packed per-pixel target record T[B,H,W,36] and, optionally, as planar tensors.
+//   be_train_pack_kernel      fills the rest of T: noisy + ground-truth pixels, log2(bndry_dist+1), z_gt, the
+//                             ground-truth derivative and Sobel(global image) (:106-110,117-118,123-124), so that the
+//                             loss kernel fetches everything about one pixel with nine 16-byte loads.
+//   be_loss_kernel<LOCAL>     one CTA walks a run of patches; per patch: phase 1 + ridge solve, render, direct dL/dP,
+//                             Sobel forward + adjoint through shared memory, A^T G + second solve, per-pixel backward to
+//                             the 14 per-patch sums, chain rule to the 12 (10) raw parameters.  Three warp-transposing
+//                             reductions per patch; no unfolded tensor, no autograd graph.
+//   be_loss_reduce_kernel     per-CTA partial sums -> the seven loss terms and the weighted loss.
+#include "be_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int T_NY = 0, T_GT = 6, T_GI = 12, T_GB = 18, T_BD = 19, T_ZG = 20, T_DGT = 24, T_DGI = 30;
+
+__device__ __forceinline__ int cover_1d(int y, int R, int s, int np) {
+    const int hi = min(y / s, np - 1);
+    const int lo = (y - R + 1 <= 0) ? 0 : (y - R + s) / s;
+    return max(hi - lo + 1, 0);
+}
+
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (hi ? v[i + 8] : v[i]) + __shfl_xor_sync(FULL, hi ? v[i] : v[i + 8], 16);
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (hi ? a[i + 4] : a[i]) + __shfl_xor_sync(FULL, hi ? a[i] : a[i + 4], 8);
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (hi ? b[i + 2] : b[i]) + __shfl_xor_sync(FULL, hi ? b[i] : b[i + 2], 4);
+    hi = lane & 2;
+    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(FULL, hi ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(FULL, d, 1);
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __restrict__ acc, BeGeom g, int B,
+                                                                 float* __restrict__ T, float* __restrict__ gimg,
+                                                                 float* __restrict__ gbnd) {
+    const size_t HW = (size_t)g.H * g.W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * HW) return;
+    const size_t p = idx % HW;
+    const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
+    const float4* src = reinterpret_cast<const float4*>(acc + idx * 8);
+    const float4 q0 = src[0], q1 = src[1];
+    const float n = (float)(cover_1d(y, g.R, g.stride, g.Hp) * cover_1d(x, g.R, g.stride, g.Wp));
+    const float v[7] = {q0.x / n, q0.y / n, q0.z / n, q0.w / n, q1.x / n, q1.y / n, q1.z / n};
+    float* t = T + idx * BE_TW;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) t[T_GI + c] = v[c];
+    t[T_GB] = v[6];
+    if (gimg) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) gimg[((size_t)b * 6 + c) * HW + p] = v[c];
+    }
+    if (gbnd) gbnd[idx] = v[6];
+}
+
+__global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, const float* __restrict__ img_ny,
+                                                            const float* __restrict__ img_gt, const float* __restrict__ bndry_dist,
+                                                            const float* __restrict__ deri, const float* __restrict__ bndry_depth,
+                                                            float* __restrict__ T) {
+    const size_t HW = (size_t)g.H * g.W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * HW) return;
+    const size_t p = idx % HW;
+    const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
+    float* t = T + idx * BE_TW;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const size_t o = (((size_t)b * 2 + m) * HW + p) * 3 + c;          // dataset-native [B,2,H,W,3]
+            t[T_NY + 3 * m + c] = img_ny[o];
+            t[T_GT + 3 * m + c] = img_gt[o];
+        }
+    t[T_BD] = log2f(bndry_dist[idx] + 1.0f);                                  // global_training.py:118
+    t[T_ZG] = bndry_depth[idx];
+    t[21] = t[22] = t[23] = 0.0f;
+    const bool interior = (y >= 1 && y < g.H - 1 && x >= 1 && x < g.W - 1);
+#pragma unroll
+    for (int mc = 0; mc < 6; ++mc) {
+        float dgt = 0.0f, dgi = 0.0f;
+        if (interior) {
+            const int m = mc / 3, c = mc % 3;
+            dgt = deri[((((size_t)b * 2 + m) * (g.H - 2) + (y - 1)) * (g.W - 2) + (x - 1)) * 3 + c];
+            // Sobel magnitude of the (already normalised) global image, utils/postprocessing_loss.py:114-117
+            const float* q = T + idx * BE_TW + T_GI + mc;
+            const long long rs = (long long)g.W * BE_TW, cs = BE_TW;
+            const float a = q[-rs - cs], bb = q[-rs], cc = q[-rs + cs], d = q[-cs], f = q[cs], gg = q[rs - cs], hh = q[rs], ii = q[rs + cs];
+            const float sx = (cc - a) + 2.0f * (f - d) + (ii - gg);
+            const float sy = (a + 2.0f * bb + cc) - (gg + 2.0f * hh + ii);
+            dgi = sqrtf(sx * sx + sy * sy + 1e-8f);
+        }
+        t[T_DGT + mc] = dgt;
+        t[T_DGI + mc] = dgi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct Slot {
+    int q, i, j;
+    bool valid, interior;
+};
+
+template <bool LOCAL>
+__global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
+    constexpr int NIMG = LOCAL ? 1 : 2;
+    constexpr int NCH = 3 * NIMG;
+    constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
+
+    __shared__ __align__(16) float s_rec[2][BE_REC];
+    __shared__ __align__(16) float s_grec[2][BE_GREC];
+    __shared__ float s_axis[BE_MAX_R + 3];
+    __shared__ float s_part[BE_WARPS][16];
+    __shared__ float s_part3[BE_WARPS][16];
+    __shared__ float s_col[9], s_V[9], s_S[6];
+    __shared__ double s_minv[6];
+    __shared__ float4 s_Pa[RRMAX];
+    __shared__ float2 s_Pb[RRMAX];
+    __shared__ float4 s_gxa[RRMAX], s_gya[RRMAX];
+    __shared__ float2 s_gxb[RRMAX], s_gyb[RRMAX];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const BeGeom g = a.g;
+    const int R = g.R, RR = R * R;
+
+    int blk = blockIdx.x;
+    const int run = blk % a.runs_per_row; blk /= a.runs_per_row;
+    const int py = blk % g.Hp;
+    const int b = blk / g.Hp;
+    const int px0 = run * a.G;
+    const int n = min(a.G, g.Wp - px0);
+    const int y0 = py * g.stride;
+    const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
+    const int np = LOCAL ? 10 : 12;
+
+    if (tid < R) s_axis[tid] = be_axis(tid, R);
+    if (tid < 8) reinterpret_cast<float4*>(s_rec[0])[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
+    if (tid >= 8 && tid < 8 + BE_GREC / 4)
+        reinterpret_cast<float4*>(s_grec[0])[tid - 8] = __ldg(reinterpret_cast<const float4*>(a.gtable + patch0 * BE_GREC) + (tid - 8));
+
+    Slot sl[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int q = tid + s * BE_THREADS;
+        sl[s].valid = q < RR;
+        sl[s].q = sl[s].valid ? q : 0;
+        sl[s].i = sl[s].q / R;
+        sl[s].j = sl[s].q % R;
+        sl[s].interior = sl[s].valid && sl[s].i >= 1 && sl[s].i <= R - 2 && sl[s].j >= 1 && sl[s].j <= R - 2;
+        if (q < RRMAX) {   // border entries of the Sobel-gradient planes stay zero for the whole kernel
+            s_gxa[q] = s_gya[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_gxb[q] = s_gyb[q] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    const float Y[2] = {s_axis[sl[0].i], s_axis[sl[1].i]};
+    const float X[2] = {s_axis[sl[0].j], s_axis[sl[1].j]};
+    const float kd = LOCAL ? 0.0f : a.gamma_d / (float)(*a.mask_count);
+
+    float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+    for (int k = 0; k < n; ++k) {
+        const int cur = k & 1;
+        const int x0 = (px0 + k) * g.stride;
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (warp == 0 && k + 1 < n) {
+            if (lane < 8) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 1) * BE_REC) + lane);
+            else if (lane < 8 + BE_GREC / 4) nxt = __ldg(reinterpret_cast<const float4*>(a.gtable + (patch0 + k + 1) * BE_GREC) + (lane - 8));
+        }
+        BePatch P;
+        {
+            const float4* q4 = reinterpret_cast<const float4*>(s_rec[cur]);
+            const float4 r0 = q4[0], r1 = q4[1], r2 = q4[2], r3 = q4[3], r4 = q4[4];
+            P.sn[0] = r0.x; P.sn[1] = r0.y; P.sn[2] = r0.z; P.sn[3] = r0.w;
+            P.cs[0] = r1.x; P.cs[1] = r1.y; P.cs[2] = r1.z; P.cs[3] = r1.w;
+            P.vx[0] = r2.x; P.vx[1] = r2.y; P.vy[0] = r2.z; P.vy[1] = r2.w;
+            P.flip[0] = r3.x; P.flip[1] = r3.y; P.z[0] = r3.z; P.z[1] = r3.w;
+            P.inv_eta[0] = r4.x; P.inv_eta[1] = r4.y; P.inv_eta[2] = r4.z; P.inv_eta[3] = r4.w;
+        }
+        // per-slot target pointers
+        const float* tp[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            tp[s] = LOCAL ? nullptr : a.T + (((size_t)b * g.H + y0 + sl[s].i) * g.W + x0 + sl[s].j) * BE_TW;
+        auto ld_ny = [&](int s, float* y) {
+            if (LOCAL) {
+                const float* p = a.l_ny + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
+                y[0] = __ldg(p); y[1] = __ldg(p + 1); y[2] = __ldg(p + 2);
+            } else {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
+                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + 4));
+                y[0] = q0.x; y[1] = q0.y; y[2] = q0.z; y[3] = q0.w; y[4] = q1.x; y[5] = q1.y;
+            }
+        };
+
+        // ---------------- stage 1: phase 1 ----------------
+        float d1[2], d2[2], h[2][2 * NIMG];
+        {
+            float sums[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sums[q] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                be_pixel_dists(P, X[s], Y[s], g.w, &d1[s], &d2[s]);
+                if (sl[s].valid) {
+                    float y[NCH];
+                    ld_ny(s, y);
+#pragma unroll
+                    for (int m = 0; m < NIMG; ++m) {
+                        const float h1 = be_h(d1[s], P.inv_eta[2 * m]), h2 = be_h(d2[s], P.inv_eta[2 * m + 1]);
+                        h[s][2 * m] = h1; h[s][2 * m + 1] = h2;
+                        float u[3];
+                        be_wedges(h1, h2, u);
+                        sums[0] = fmaf(u[0], u[0], sums[0]); sums[1] = fmaf(u[0], u[1], sums[1]); sums[2] = fmaf(u[0], u[2], sums[2]);
+                        sums[3] = fmaf(u[1], u[1], sums[3]); sums[4] = fmaf(u[1], u[2], sums[4]); sums[5] = fmaf(u[2], u[2], sums[5]);
+#pragma unroll
+                        for (int wd = 0; wd < 3; ++wd)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) sums[6 + 3 * wd + c] = fmaf(u[wd], y[3 * m + c], sums[6 + 3 * wd + c]);
+                    }
+                }
+            }
+            const float tot = warp_reduce16(sums, lane);
+            if (!(lane & 1)) s_part[warp][lane >> 1] = tot;
+        }
+        __syncthreads();   // (1)
+
+        // ---------------- stage 2: ridge solve (warp 0, fp64) ----------------
+        if (warp == 0) {
+            float t = 0.0f;
+            if (lane < 16) {
+#pragma unroll
+                for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part[wv][lane];
+            }
+            float S[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) S[q] = __shfl_sync(FULL, t, q);
+            double Minv[6];
+            float C[9];
+            be_solve_colors(S, g.lam, Minv, C);
+            if (lane == 0) {   // static indices only: a lane-indexed register array would live in local memory
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s_col[q] = C[q];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s_minv[q] = Minv[q];
+            }
+            if (k + 1 < n) {
+                if (lane < 8) reinterpret_cast<float4*>(s_rec[cur ^ 1])[lane] = nxt;
+                else if (lane < 8 + BE_GREC / 4) reinterpret_cast<float4*>(s_grec[cur ^ 1])[lane - 8] = nxt;
+            }
+        }
+        __syncthreads();   // (2)
+
+        // ---------------- stage 3: render, direct dL/dP ----------------
+        float C[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) C[q] = s_col[q];
+        float G[2][NCH];
+        float gbv[2] = {0.f, 0.f}, bdv[2] = {0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (sl[s].valid) {
+                float Pv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int m = 0; m < NIMG; ++m) {
+                    float u[3];
+                    be_wedges(h[s][2 * m], h[s][2 * m + 1], u);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Pv[3 * m + c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                }
+                s_Pa[sl[s].q] = make_float4(Pv[0], Pv[1], Pv[2], Pv[3]);
+                s_Pb[sl[s].q] = make_float2(Pv[4], Pv[5]);
+                if (LOCAL) {
+                    const float* p = a.l_gt + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float e1 = Pv[c] - __ldg(p + c);
+                        lossacc[0] = fmaf(e1, e1, lossacc[0]);
+                        G[s][c] = 2.0f * a.kc * e1;
+                    }
+                    bdv[s] = __ldg(a.l_bd + ((size_t)b * R + sl[s].i) * R + sl[s].j);
+                } else {
+                    const float2 t1 = __ldg(reinterpret_cast<const float2*>(tp[s] + 6));
+                    const float4 t2 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8));
+                    const float4 t3 = __ldg(reinterpret_cast<const float4*>(tp[s] + 12));
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp[s] + 16));
+                    const float gt[6] = {t1.x, t1.y, t2.x, t2.y, t2.z, t2.w};
+                    const float gi[6] = {t3.x, t3.y, t3.z, t3.w, t4.x, t4.y};
+                    gbv[s] = t4.z; bdv[s] = t4.w;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        const float e1 = Pv[c] - gt[c], e2 = Pv[c] - gi[c];
+                        lossacc[0] = fmaf(e1, e1, lossacc[0]);
+                        lossacc[1] = fmaf(e2, e2, lossacc[1]);
+                        G[s][c] = 2.0f * (a.kc * e1 + a.kcc * e2);
+                    }
+                }
+            }
+        }
+        __syncthreads();   // (3)
+
+        // ---------------- stage 4: Sobel magnitude of the rendered patch, its loss and gradient ----------------
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (sl[s].interior) {
+                float sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sy[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int oi = -1; oi <= 1; ++oi)
+#pragma unroll
+                    for (int oj = -1; oj <= 1; ++oj) {
+                        if (oi == 0 && oj == 0) continue;
+                        const float wx = (float)(((oi == 0) ? 2 : 1) * oj);       // sobel_x[oi+1][oj+1]
+                        const float wy = (float)(-oi * ((oj == 0) ? 2 : 1));      // sobel_y[oi+1][oj+1]
+                        const int qn = sl[s].q + oi * R + oj;
+                        const float4 pa = s_Pa[qn];
+                        const float2 pb = s_Pb[qn];
+                        const float pv[6] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y};
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) {
+                            if (wx != 0.0f) sx[c] = fmaf(wx, pv[c], sx[c]);
+                            if (wy != 0.0f) sy[c] = fmaf(wy, pv[c], sy[c]);
+                        }
+                    }
+                float dgt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dgi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (LOCAL) {
+                    const float* p = a.l_deri + (((size_t)b * (R - 2) + sl[s].i - 1) * (R - 2) + sl[s].j - 1) * 3;
+                    dgt[0] = __ldg(p); dgt[1] = __ldg(p + 1); dgt[2] = __ldg(p + 2);
+                } else {
+                    const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 24));
+                    const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 28));
+                    const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 32));
+                    dgt[0] = t6.x; dgt[1] = t6.y; dgt[2] = t6.z; dgt[3] = t6.w; dgt[4] = t7.x; dgt[5] = t7.y;
+                    dgi[0] = t7.z; dgi[1] = t7.w; dgi[2] = t8.x; dgi[3] = t8.y; dgi[4] = t8.z; dgi[5] = t8.w;
+                }
+                float gx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gy[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const float v = fmaf(sx[c], sx[c], fmaf(sy[c], sy[c], 1e-8f));
+                    const float ir = rsqrtf(v);
+                    const float mag = v * ir;
+                    const float e1 = mag - dgt[c];
+                    lossacc[3] = fmaf(e1, e1, lossacc[3]);
+                    float gm = 2.0f * a.ks * e1;
+                    if (!LOCAL) {
+                        const float e2 = mag - dgi[c];
+                        lossacc[4] = fmaf(e2, e2, lossacc[4]);
+                        gm = fmaf(2.0f * a.ksc, e2, gm);
+                    }
+                    gx[c] = gm * sx[c] * ir;
+                    gy[c] = gm * sy[c] * ir;
+                }
+                s_gxa[sl[s].q] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+                s_gxb[sl[s].q] = make_float2(gx[4], gx[5]);
+                s_gya[sl[s].q] = make_float4(gy[0], gy[1], gy[2], gy[3]);
+                s_gyb[sl[s].q] = make_float2(gy[4], gy[5]);
+            }
+        }
+        __syncthreads();   // (4)
+
+        // ---------------- stage 5: Sobel adjoint into G, then A^T G ----------------
+        {
+            float sums[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sums[q] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (sl[s].valid) {
+#pragma unroll
+                    for (int di = -1; di <= 1; ++di)
+#pragma unroll
+                        for (int dj = -1; dj <= 1; ++dj) {
+                            if (di == 0 && dj == 0) continue;
+                            const int io = sl[s].i + di, jo = sl[s].j + dj;
+                            if (io < 0 || io >= R || jo < 0 || jo >= R) continue;
+                            const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
+                            const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
+                            const int qn = sl[s].q + di * R + dj;
+                            if (wx != 0.0f) {
+                                const float4 ga = s_gxa[qn];
+                                const float2 gb = s_gxb[qn];
+                                const float gv[6] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y};
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) G[s][c] = fmaf(wx, gv[c], G[s][c]);
+                            }
+                            if (wy != 0.0f) {
+                                const float4 ga = s_gya[qn];
+                                const float2 gb = s_gyb[qn];
+                                const float gv[6] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y};
+#pragma unroll
+                                for (int c = 0; c < NCH; ++c) G[s][c] = fmaf(wy, gv[c], G[s][c]);
+                            }
+                        }
+#pragma unroll
+                    for (int m = 0; m < NIMG; ++m) {
+                        float u[3];
+                        be_wedges(h[s][2 * m], h[s][2 * m + 1], u);
+#pragma unroll
+                        for (int wd = 0; wd < 3; ++wd)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) sums[3 * wd + c] = fmaf(u[wd], G[s][3 * m + c], sums[3 * wd + c]);
+                    }
+                }
+            }
+            const float tot = warp_reduce16(sums, lane);
+            if (!(lane & 1)) s_part[warp][lane >> 1] = tot;
+        }
+        __syncthreads();   // (5)
+
+        // ---------------- stage 6: second solve (warp 0) ----------------
+        if (warp == 0) {
+            float t = 0.0f;
+            if (lane < 16) {
+#pragma unroll
+                for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part[wv][lane];
+            }
+            float AtG[9], V[9], Ssym[6];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) AtG[q] = __shfl_sync(FULL, t, q);
+            double Minv[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) Minv[q] = s_minv[q];
+            be_backsolve(Minv, AtG, C, V, Ssym);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s_V[q] = V[q];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s_S[q] = Ssym[q];
+            }
+        }
+        __syncthreads();   // (6)
+
+        // ---------------- stage 7: per-pixel backward -> 14 per-patch sums ----------------
+        {
+            float V[9], Ssym[6];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) V[q] = s_V[q];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) Ssym[q] = s_S[q];
+            float sums[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sums[q] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (sl[s].valid) {
+                    float y[NCH];
+                    ld_ny(s, y);
+                    float gd1 = 0.0f, gd2 = 0.0f;
+#pragma unroll
+                    for (int m = 0; m < NIMG; ++m) {
+                        float u[3], gu[3], gh1, gh2, da, de;
+                        const float h1 = h[s][2 * m], h2 = h[s][2 * m + 1];
+                        be_wedges(h1, h2, u);
+                        be_ridge_backward_pixel(&G[s][3 * m], &y[3 * m], u, C, V, Ssym, gu);
+                        be_wedges_backward(h1, h2, gu, &gh1, &gh2);
+                        be_h_grad(d1[s], P.inv_eta[2 * m], &da, &de);
+                        gd1 = fmaf(gh1, da, gd1); sums[8 + 2 * m] = fmaf(gh1, de, sums[8 + 2 * m]);
+                        be_h_grad(d2[s], P.inv_eta[2 * m + 1], &da, &de);
+                        gd2 = fmaf(gh2, da, gd2); sums[9 + 2 * m] = fmaf(gh2, de, sums[9 + 2 * m]);
+                    }
+                    const float lb = be_boundary(d1[s], d2[s]);
+                    const float bl = bdv[s] * lb;
+                    lossacc[5] = fmaf(bl, bl, lossacc[5]);
+                    float glb = 2.0f * a.kbl * bdv[s] * bl;
+                    if (!LOCAL) {
+                        const float e = lb - gbv[s];
+                        lossacc[2] = fmaf(e, e, lossacc[2]);
+                        glb = fmaf(2.0f * a.kbc, e, glb);
+                        const float zgv = __ldg(tp[s] + T_ZG);
+                        const int mk = be_mask(d1[s], d2[s], false);
+                        if (zgv != 0.0f && mk != 0) {
+                            const float e2 = ((mk == 1) ? P.z[0] : P.z[1]) - zgv;
+                            lossacc[6] = fmaf(e2, e2, lossacc[6]);
+                            if (mk == 1) sums[12] = fmaf(2.0f * kd, e2, sums[12]);
+                            else sums[13] = fmaf(2.0f * kd, e2, sums[13]);
+                        }
+                    }
+                    be_boundary_backward(d1[s], d2[s], lb, glb, &gd1, &gd2);
+                    be_wedge_backward(P, 0, X[s], Y[s], g.w, gd1, &sums[0]);
+                    be_wedge_backward(P, 1, X[s], Y[s], g.w, gd2, &sums[4]);
+                }
+            }
+            const float tot = warp_reduce16(sums, lane);
+            if (!(lane & 1)) s_part3[warp][lane >> 1] = tot;
+        }
+        __syncthreads();   // (7)
+
+        // ---------------- stage 8: chain rule to the raw parameters (warp 0) ----------------
+        if (warp == 0 && a.grad != nullptr) {
+            float t = 0.0f;
+            if (lane < 16) {
+#pragma unroll
+                for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part3[wv][lane];
+            }
+            float S[14];
+#pragma unroll
+            for (int q = 0; q < 14; ++q) S[q] = __shfl_sync(FULL, t, q);
+            if (lane == 0) {
+                const float* gr = s_grec[cur];      // deta_dcoef[4], dz_deta[4], xy_scale, ang_scale
+                float* out = a.grad + (patch0 + k) * np;
+                const float xs = gr[8], as = gr[9];
+                out[0] = xs * S[0]; out[1] = xs * S[1]; out[2] = xs * S[4]; out[3] = xs * S[5];
+                out[4] = as * (S[2] + S[3]); out[5] = as * S[3]; out[6] = as * (S[6] + S[7]); out[7] = as * S[7];
+                if (LOCAL) {
+                    out[8] = S[8] * gr[0]; out[9] = S[9] * gr[1];
+                } else {
+                    out[8] = (S[8] + S[12] * gr[4]) * gr[0];
+                    out[9] = (S[9] + S[13] * gr[6]) * gr[1];
+                    out[10] = (S[10] + S[12] * gr[5]) * gr[2];
+                    out[11] = (S[11] + S[13] * gr[7]) * gr[3];
+                }
+            }
+        }
+    }
+
+    // ---------------- per-CTA partial loss sums ----------------
+    {
+        float sums[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sums[q] = (q < 7) ? lossacc[q] : 0.0f;
+        const float tot = warp_reduce16(sums, lane);
+        __syncthreads();
+        if (!(lane & 1)) s_part[warp][lane >> 1] = tot;
+        __syncthreads();
+        if (tid < 8) {
+            float t = 0.0f;
+#pragma unroll
+            for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part[wv][tid];
+            a.partials[(size_t)blockIdx.x * 8 + tid] = t;
+        }
+    }
+}
+
+// partial sums -> terms (unweighted, as the oracle's `terms`) and the weighted loss
+__global__ void __launch_bounds__(256) be_loss_reduce_kernel(const float* __restrict__ partials, int nblocks, BeLossScale sc,
+                                                             const unsigned long long* __restrict__ mask_count,
+                                                             float* __restrict__ terms, float* __restrict__ loss) {
+    __shared__ double s[256][7];
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x)
+#pragma unroll
+        for (int t = 0; t < 7; ++t) acc[t] += (double)partials[(size_t)i * 8 + t];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) s[threadIdx.x][t] = acc[t];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+#pragma unroll
+            for (int t = 0; t < 7; ++t) s[threadIdx.x][t] += s[threadIdx.x + off][t];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double l = 0.0;
+        for (int t = 0; t < sc.nterms; ++t) {
+            const int src = sc.src[t];
+            double v = s[0][src] * sc.scale[t];
+            if (sc.masked[t]) v = s[0][src] / (double)(*mask_count);     // 0/0 -> NaN, as the reference (global_training.py:127)
+            terms[t] = (float)v;
+            l += (double)sc.gamma[t] * v;
+        }
+        *loss = (float)l;
+    }
+}
+
+}  // namespace
+
+void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st) {
+    const size_t n = (size_t)B * g.H * g.W;
+    be_train_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, B, T, gimg, gbnd);
+    ++g_be_launches;
+}
+
+void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
+                          const float* bndry_depth, float* T, cudaStream_t st) {
+    const size_t n = (size_t)B * g.H * g.W;
+    be_train_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, B, img_ny, img_gt, bndry_dist, deri, bndry_depth, T);
+    ++g_be_launches;
+}
+
+void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st) {
+    const int grid = a.NB * a.g.Hp * a.runs_per_row;
+    if (local) be_loss_kernel<true><<<grid, BE_THREADS, 0, st>>>(a);
+    else be_loss_kernel<false><<<grid, BE_THREADS, 0, st>>>(a);
+    ++g_be_launches;
+}
+
+void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
+                           float* loss, cudaStream_t st) {
+    be_loss_reduce_kernel<<<1, 256, 0, st>>>(partials, nblocks, sc, mask_count, terms, loss);
+    ++g_be_launches;
+}

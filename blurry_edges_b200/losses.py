@@ -1,0 +1,164 @@
+"""Fused siblings of the training criteria of the reference:
+
+  GlobalLossFused  ==  global_training.GlobalLoss   (global_training.py:11-157)
+  LocalLossFused   ==  local_training.LocalLoss     (local_training.py:10-52)
+
+Same constructor arguments, same gamma / beta schedules, same `forward` signatures; the loss and its gradient w.r.t. the
+network output are produced by the sm_100a kernels of csrc/be_train.cu (forward + analytic backward in one pass) and
+handed to autograd through a tiny torch.autograd.Function."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .fused import _geometry_from_args
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """loss = f(est) with the gradient already computed by the kernel; backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, est, loss, grad):
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None
+
+
+class GlobalLossFused(nn.Module):
+    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None):
+        super().__init__()
+        self.device = torch.device(device)
+        self.depthCal = depthCal
+        self.R, self.stride, self.w = int(args.R), int(args.stride), float(args.w)
+        self.batch_size = int(args.batch_size)
+        self.H, self.W = int(args.img_size[0]), int(args.img_size[1])
+        # global_training.py:14-22
+        self.dynamic_epoch = args.dynamic_epoch
+        self.gamma_color_range = args.gamma_color
+        self.gamma_color_cons_range = args.gamma_color_cons
+        self.gamma_bndry_cons_range = args.gamma_bndry_cons
+        self.gamma_smthns_range = args.gamma_smthns
+        self.gamma_smthns_cons_range = args.gamma_smthns_cons
+        self.gamma_bndry_loc_range = args.gamma_bndry_loc
+        self.gamma_depth_range = args.gamma_depth
+        self.gamma_idx = -1
+        self.process_group = process_group      # data-parallel: ranks hold disjoint slices of the global batch
+        self._geo = _geometry_from_args(args)
+        self.ctx = _lib.Context(_lib.make_config(max_batch=self.batch_size, **self._geo), self.device)
+        self.H_patches, self.W_patches = self.ctx.Hp, self.ctx.Wp
+        self.lambda_ridge = self.ctx.lambda_ridge
+        self.global_image = self.global_bndry = self.terms = None
+
+    _RANGES = ('gamma_color', 'gamma_color_cons', 'gamma_bndry_cons', 'gamma_smthns', 'gamma_smthns_cons', 'gamma_bndry_loc', 'gamma_depth')
+
+    def calculate_gamma(self, gamma_range, rate, order=1):      # global_training.py:25-26
+        return gamma_range[0] + rate ** order * (gamma_range[1] - gamma_range[0])
+
+    def update_gamma(self, idx_update=True):                     # global_training.py:28-51
+        if idx_update:
+            self.gamma_idx += 1
+        e0, e1, e2 = self.dynamic_epoch
+        if self.gamma_idx < e0:
+            rate, k = self.gamma_idx / (e0 - 1), 0
+        elif self.gamma_idx < e1:
+            rate, k = 1.0, 0
+        elif self.gamma_idx < e2:
+            rate, k = (self.gamma_idx - e1) / (e2 - e1 - 1), 1
+        else:
+            rate, k = 1.0, 1
+        for name in self._RANGES:
+            setattr(self, name, self.calculate_gamma(getattr(self, name + '_range')[k:k + 2], rate))
+
+    def final_gamma(self):                                       # global_training.py:53-60
+        for name in self._RANGES:
+            setattr(self, name, getattr(self, name + '_range')[-1])
+
+    def gammas(self):
+        return [getattr(self, name) for name in self._RANGES]
+
+    def _f32(self, t):
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def forward(self, est, img_ny, img_gt, bndry_dist, deri, bndry_depth):
+        """est [B,L,12] raw GlobalStage output; img_ny / img_gt [B,2,H,W,3]; bndry_dist / bndry_depth [B,H,W];
+        deri [B,2,H-2,W-2,3] (global_training.py:147-157).  Returns the scalar loss (differentiable w.r.t. est)."""
+        B, L = est.shape[0], self.ctx.L
+        if est.dim() != 3 or est.shape[1:] != (L, 12):
+            raise _lib.BlurryEdgesError(f'expects est [B,{L},12], got {tuple(est.shape)}')
+        if B > self.ctx.max_batch:
+            self.ctx.close()
+            self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
+        raw = self._f32(est.detach())
+        ny, gt = self._f32(img_ny), (img_ny if img_gt is img_ny else img_gt)
+        gt = ny if gt is img_ny else self._f32(gt)
+        want_grad = torch.is_grad_enabled() and est.requires_grad
+        gimg, gbnd, cnt = self.ctx.global_loss_stage1(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self._f32(bndry_depth))
+        npatch = B * L
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(cnt, group=self.process_group)      # depth normaliser over the WHOLE batch (global_training.py:127)
+            npatch *= dist.get_world_size(self.process_group)
+        terms, loss, grad = self.ctx.global_loss_stage2(B, self.gammas(), npatch, cnt, want_grad)
+        self.global_image, self.global_bndry, self.terms, self.mask_count = gimg, gbnd, terms, cnt
+        if want_grad:
+            return _FusedLossFn.apply(est, loss, grad.to(est.dtype))
+        return loss.reshape(())
+
+
+class LocalLossFused(nn.Module):
+    def __init__(self, args, device='cuda:0'):
+        super().__init__()
+        self.device = torch.device(device)
+        self.R, self.w = int(args.R), float(args.w)
+        self.batch_size = int(args.batch_size)
+        self.max_beta_bndry_loc = args.beta_bndry_loc       # local_training.py:13-16
+        self.max_beta_smthns = args.beta_smthns
+        self.beta_idx = -1
+        self.dynamic_epoch = args.dynamic_epoch
+        self._geo = dict(R=self.R, stride=1, H=self.R, W=self.R, w=self.w, alpha_lambda=float(args.alpha_lambda),
+                         cam=dict(args.cam_params), mag=float(args.mag))
+        self.ctx = _lib.Context(_lib.make_config(max_batch=self.batch_size, **self._geo), self.device)
+        self.lambda_ridge = self.ctx.lambda_ridge
+        self.terms = None
+
+    def update_beta(self, idx_update=True):                  # local_training.py:18-26
+        if idx_update:
+            self.beta_idx += 1
+        rate = self.beta_idx / (self.dynamic_epoch - 1) if self.beta_idx < self.dynamic_epoch else 1.0
+        self.beta_bndry_loc = rate * self.max_beta_bndry_loc
+        self.beta_smthns = rate * self.max_beta_smthns
+
+    def final_beta(self):                                    # local_training.py:28-30
+        self.beta_bndry_loc = self.max_beta_bndry_loc
+        self.beta_smthns = self.max_beta_smthns
+
+    def _f32(self, t):
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def forward(self, est, img_ny, gt_img, bndry_dist, deri):
+        """est [B,10] raw LocalStage output; img_ny / gt_img [B,R,R,3]; bndry_dist [B,R,R]; deri [B,R-2,R-2,3]
+        (local_training.py:47-52).  Like the reference (:33) the angles of `est` are wrapped IN PLACE."""
+        B = est.shape[0]
+        if est.dim() != 2 or est.shape[1] != 10:
+            raise _lib.BlurryEdgesError(f'expects est [B,10], got {tuple(est.shape)}')
+        if B > self.ctx.max_batch:
+            self.ctx.close()
+            self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
+        raw = self._f32(est.detach())
+        want_grad = torch.is_grad_enabled() and est.requires_grad
+        ny = self._f32(img_ny)
+        gt = ny if gt_img is img_ny else self._f32(gt_img)
+        terms, loss, grad = self.ctx.local_loss(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self.beta_bndry_loc,
+                                                self.beta_smthns, want_grad)
+        self.terms = terms
+        with torch.no_grad():                                # the reference mutates the network output (local_training.py:33)
+            if not (est.requires_grad and est.is_leaf):
+                est.data[:, 4:8] = torch.remainder(est.data[:, 4:8], 2 * torch.pi)
+        if want_grad:
+            return _FusedLossFn.apply(est, loss, grad.to(est.dtype))
+        return loss.reshape(())

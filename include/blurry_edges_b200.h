@@ -93,6 +93,29 @@ int be_host_render_fold(be_ctx* ctx, const float* est, int32_t param_mode, const
                         float* image, float* sharp, float* refoc, float* bndry, float* depth, float* conf,
                         float* depth_thresholded);
 
+/* GlobalLoss.forward + backward (global_training.py:62-157), in two stages so that a data-parallel caller can all-reduce
+ * the depth-term normaliser between them (the depth term divides by the mask count of the WHOLE batch, :127).
+ * Layouts are the dataset's (data/dataset.py:50-56): raw [B,L,12] network output, img_ny/img_gt [B,2,H,W,3],
+ * bndry_dist / bndry_depth [B,H,W], deri [B,2,H-2,W-2,3].
+ * stage1: split_restore_params, render both images with shared colours + boundary, fold -> global_image [B,2,3,H,W] and
+ *         global_bndry [B,1,H,W] (may be NULL; they are detached targets), mask count -> dev_mask_count (one int64).
+ * stage2: the seven loss terms (unweighted, [7]) and loss = sum gamma_k term_k ([1]); if dev_grad != NULL also
+ *         d loss / d raw [B,L,12], computed analytically per patch (every folded target is detached in the reference).
+ *         global_patches = (global batch) * L; dev_mask_count may have been summed over ranks by the caller. */
+int be_global_loss_stage1(be_ctx* ctx, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                          const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                          float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream);
+int be_global_loss_stage2(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                          float* dev_terms, float* dev_loss, float* dev_grad, void* stream);
+
+/* LocalLoss.forward + backward (local_training.py:32-52): est [B,10] raw LocalStage output (angles wrapped inside),
+ * img_ny / img_gt [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation,
+ * smoothness), loss [1] = terms[0] + beta_bndry_loc * terms[1] + beta_smthns * terms[2], grad [B,10] (may be NULL).
+ * Needs a context created with H = W = R. */
+int be_local_loss(be_ctx* ctx, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
+                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, float* dev_terms, float* dev_loss,
+                  float* dev_grad, void* stream);
+
 /* Measurement hook: with timing enabled, be_render_fold_fwd brackets each of its four device operations with CUDA
  * events on the caller's stream; be_ctx_last_timing waits for the last call and returns their durations in ms:
  * ms4 = {accumulator memset, be_setup_kernel, be_run_kernel, be_normalise_kernel}. */

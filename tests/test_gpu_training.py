@@ -1,0 +1,185 @@
+"""GPU parity tests of the training criteria (GlobalLossFused / LocalLossFused, forward + analytic backward) against
+autograd through the fp64 oracle and against the golden vectors produced by the unmodified reference.
+
+Tolerances: loss / terms 5e-6 relative; gradients max|g - g64| <= 5e-5 max|g64| and rel-L2 <= 2e-5 for realistic
+parameters (eta >= 0.016).  The reference's own fp32 gradients are 1e-4 rel-L2 away from its fp64 gradients."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from common import F32, F64, GEOMS, Golden, geom, gloss_inputs, relmax
+from oracle import be_oracle as O
+
+pytestmark = pytest.mark.gpu
+CAM = O.Camera()
+CAMP = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
+RANGES = dict(gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
+              gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
+              gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200])           # utils/args.py:53-63
+NAMES = ('gamma_color', 'gamma_color_cons', 'gamma_bndry_cons', 'gamma_smthns', 'gamma_smthns_cons', 'gamma_bndry_loc', 'gamma_depth')
+
+
+def _gargs(S, B):
+    return argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[S, S], batch_size=B, mag=4.0, cam_params=CAMP, **RANGES)
+
+
+def _grad_err(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(got - ref).max() / np.abs(ref).max()), float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+
+
+def _set_gammas(crit, gam):
+    for n, v in zip(NAMES, gam):
+        setattr(crit, n, float(v))
+
+
+def _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt):
+    est = raw.clone().cuda().requires_grad_(True)
+    loss = crit(est, img_ny.cuda(), img_gt.cuda(), bd.cuda(), deri.cuda(), zgt.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), est.grad.cpu().numpy(), crit.terms.cpu().numpy()
+
+
+@pytest.mark.parametrize('gname', list(GEOMS))
+@pytest.mark.parametrize('gset', ['idx0', 'final'] + [f'only{k}' for k in range(7)])
+def test_global_loss_vs_oracle_and_golden(gname, gset):
+    from blurry_edges_b200 import GlobalLossFused
+    gold = Golden('global_loss')
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs(gname, 'normal', F32)
+    gam = gold(f'{gname}/gloss/normal/{gset}/f64/gammas')
+    crit = GlobalLossFused(_gargs(GEOMS[gname], 2), None, 'cuda:0')
+    crit.update_gamma()
+    if gset == 'idx0':
+        np.testing.assert_allclose(crit.gammas(), gam, rtol=0, atol=0)      # schedule mirrors global_training.py:28-51
+    _set_gammas(crit, gam)
+    loss, grad, terms = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    r64 = raw.to(F64).requires_grad_(True)
+    l64, t64, aux = O.global_loss(r64, img_ny.to(F64), img_gt.to(F64), bd.to(F64), deri.to(F64), zgt.to(F64), gam, g, CAM, return_terms=True)
+    (g64,) = torch.autograd.grad(l64, r64)
+    assert abs(loss - l64.item()) <= 5e-6 * abs(l64.item())
+    np.testing.assert_allclose(terms, t64.detach().numpy(), rtol=5e-6)
+    emax, el2 = _grad_err(grad, g64.numpy())
+    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)
+    assert relmax(crit.global_image.cpu().numpy(), aux['gimg'].numpy()) < 1e-5
+    assert relmax(crit.global_bndry.cpu().numpy(), aux['gbnd'].numpy()) < 1e-5
+    # the unmodified reference (fp64): same inputs up to the fp32 rounding of nothing (inputs are fp32-exact)
+    assert abs(loss - float(gold(f'{gname}/gloss/normal/{gset}/f64/loss'))) <= 5e-6 * abs(loss)
+    emax, el2 = _grad_err(grad, gold(f'{gname}/gloss/normal/{gset}/f64/grad'))
+    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)
+
+
+def test_global_loss_stress_parameters_within_fp32_noise_floor():
+    """U[-1,1] raw parameters (eta down to 1e-3): bound = the error of fp32 autograd through the oracle itself."""
+    from blurry_edges_b200 import GlobalLossFused
+    gold = Golden('global_loss')
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('mid', 'stress', F32)
+    gam = gold('mid/gloss/stress/idx0/f64/gammas')
+    crit = GlobalLossFused(_gargs(GEOMS['mid'], 2), None, 'cuda:0')
+    _set_gammas(crit, gam)
+    loss, grad, _ = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    g64 = gold('mid/gloss/stress/idx0/f64/grad')
+    r32 = raw.clone().requires_grad_(True)
+    (g32,) = torch.autograd.grad(O.global_loss(r32, img_ny, img_gt, bd, deri, zgt, gam, g, CAM), r32)
+    floor, floor2 = _grad_err(g32.numpy(), g64)
+    emax, el2 = _grad_err(grad, g64)
+    assert abs(loss - float(gold('mid/gloss/stress/idx0/f64/loss'))) <= 2e-5 * abs(loss)
+    assert emax < max(5e-5, 2 * floor) and el2 < max(2e-5, 2 * floor2), (emax, el2, floor, floor2)
+
+
+def test_global_loss_no_grad_and_eval_mode():
+    from blurry_edges_b200 import GlobalLossFused
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('tiny', 'normal', F32)
+    crit = GlobalLossFused(_gargs(GEOMS['tiny'], 2), None, 'cuda:0')
+    crit.final_gamma()
+    with torch.no_grad():
+        l0 = crit(raw.cuda(), img_ny.cuda(), img_gt.cuda(), bd.cuda(), deri.cuda(), zgt.cuda())
+    assert not l0.requires_grad
+    l1, _, _ = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    assert abs(l0.item() - l1) <= 1e-7 * abs(l1)
+
+
+def test_global_loss_batch_split_matches_full_batch():
+    """Data-parallel semantics without NCCL: two half batches, mask counts summed between the stages, global patch
+    count in the normalisers -> loss and gradients of the full batch (the depth term divides by the WHOLE batch's mask
+    count, global_training.py:127)."""
+    from blurry_edges_b200 import GlobalLossFused
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('mid', 'normal', F32, B=4)
+    gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 0.5]
+    crit = GlobalLossFused(_gargs(GEOMS['mid'], 4), None, 'cuda:0')
+    _set_gammas(crit, gam)
+    loss, grad, terms = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    dev = lambda t: t.cuda().contiguous()
+    halves = [crit.__class__(_gargs(GEOMS['mid'], 2), None, 'cuda:0') for _ in range(2)]
+    cnts, part = [], []
+    for k, h in enumerate(halves):
+        sl = slice(2 * k, 2 * k + 2)
+        _, _, c = h.ctx.global_loss_stage1(dev(raw[sl]), dev(img_ny[sl]), dev(img_gt[sl]), dev(bd[sl]), dev(deri[sl]), dev(zgt[sl]))
+        cnts.append(c)
+    total = cnts[0] + cnts[1]
+    for h in halves:
+        part.append(h.ctx.global_loss_stage2(2, gam, 4 * g.L, total, True))
+    # unmasked terms are means over the global batch -> partial terms add up; the masked term adds up too (same divisor)
+    t_sum = (part[0][0] + part[1][0]).cpu().numpy()
+    np.testing.assert_allclose(t_sum, terms, rtol=2e-6)
+    assert abs((part[0][1] + part[1][1]).item() - loss) <= 2e-6 * abs(loss)
+    g_cat = torch.cat([part[0][2], part[1][2]]).cpu().numpy()
+    assert relmax(g_cat, grad) < 2e-6
+
+
+def test_global_loss_full_size_one_pair_vs_oracle():
+    """Config 3 geometry (147x147, 4096 patches): one pair against autograd through the fp64 oracle."""
+    from blurry_edges_b200 import GlobalLossFused
+    S = 147
+    g = geom(S)
+    img_ny = synth.image_pairs(1, S, S, seed=31)
+    img_gt, bd, deri, zgt = synth.loss_targets(1, S, S, seed=31)
+    raw = synth.raw_global(1, g.L, seed=33)
+    gam = O.gamma_schedule(0, [RANGES[n] for n in NAMES])
+    crit = GlobalLossFused(_gargs(S, 1), None, 'cuda:0')
+    crit.update_gamma()
+    loss, grad, terms = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    r64 = raw.to(F64).requires_grad_(True)
+    l64, t64, _ = O.global_loss(r64, img_ny.to(F64), img_gt.to(F64), bd.to(F64), deri.to(F64), zgt.to(F64), gam, g, CAM, return_terms=True)
+    (g64,) = torch.autograd.grad(l64, r64)
+    assert abs(loss - l64.item()) <= 5e-6 * abs(l64.item())
+    np.testing.assert_allclose(terms, t64.detach().numpy(), rtol=5e-6)
+    emax, el2 = _grad_err(grad, g64.numpy())
+    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)
+
+
+@pytest.mark.parametrize('name', ['final', 'loc', 'smth'])
+def test_local_loss_vs_oracle_and_golden(name):
+    from blurry_edges_b200 import LocalLossFused
+    gl = Golden('local_loss')
+    g = geom(147)
+    est, ny, gt, bd, deri = synth.local_batch(8, 21, seed=41)
+    betas = gl(f'lloss/{name}/f64/betas')
+    args = argparse.Namespace(R=21, w=1.0, alpha_lambda=5e-3, batch_size=8, mag=4.0, cam_params=CAMP, beta_bndry_loc=0.001,
+                              beta_smthns=0.0005, dynamic_epoch=200)
+    crit = LocalLossFused(args, 'cuda:0')
+    crit.final_beta()
+    if name == 'final':
+        assert (crit.beta_bndry_loc, crit.beta_smthns) == tuple(betas)
+    crit.beta_bndry_loc, crit.beta_smthns = float(betas[0]), float(betas[1])
+    leaf = est.clone().cuda().requires_grad_(True)
+    out = leaf * 1.0                                              # network output stand-in (non-leaf, as in local_training.py:102)
+    loss = crit(out, ny.cuda(), gt.cuda(), bd.cuda(), deri.cuda())
+    loss.backward()
+    grad = leaf.grad.cpu().numpy()
+    # like the reference (local_training.py:33) the angles of the network output are wrapped in place
+    assert torch.allclose(out.detach().cpu()[:, 4:8], torch.remainder(est[:, 4:8], 2 * torch.pi))
+    assert abs(loss.item() - float(gl(f'lloss/{name}/f64/loss'))) <= 5e-6 * abs(loss.item())
+    e64 = est.to(F64).requires_grad_(True)
+    l64, t64, _ = O.local_loss(e64, ny.to(F64), gt.to(F64), bd.to(F64), deri.to(F64), betas, g, return_terms=True)
+    (g64,) = torch.autograd.grad(l64, e64)
+    np.testing.assert_allclose(crit.terms.cpu().numpy(), t64.detach().numpy(), rtol=5e-6)
+    e32 = est.clone().requires_grad_(True)
+    (g32,) = torch.autograd.grad(O.local_loss(e32, ny, gt, bd, deri, betas, g), e32)
+    floor, _ = _grad_err(g32.numpy(), g64.numpy())
+    for ref in (g64.numpy(), gl(f'lloss/{name}/f64/grad')):
+        emax, _ = _grad_err(grad, ref)
+        assert emax < max(2e-5, 2 * floor), (emax, floor)         # eta reaches 1.6e-3 in this fixture: fp32 noise floor applies
