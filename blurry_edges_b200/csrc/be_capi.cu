@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -118,6 +119,12 @@ int validate_cfg(const be_config* cfg) {
     BE_REQUIRE(cfg->stride >= 1 && cfg->stride < cfg->R, "stride=%d must be in [1,R)", cfg->stride);
     BE_REQUIRE(cfg->H >= cfg->R && cfg->W >= cfg->R, "image %dx%d smaller than the patch", cfg->H, cfg->W);
     return 0;
+}
+
+// BE_RUN_V=1 selects the first-generation renderer (A/B measurements only)
+void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) {
+    static const int v = [] { const char* e = getenv("BE_RUN_V"); return e ? atoi(e) : 2; }();
+    if (v == 1) be_launch_run(mode, a, st); else be_launch_run2(mode, a, st);
 }
 
 int pick_runs(const BeGeom& g, int* G, int* runs) {
@@ -242,7 +249,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
     a.g = c->g; a.cam = c->cam; a.NB = M;
     pick_runs(c->g, &a.G, &a.runs_per_row);
-    be_launch_run(BE_RUN_COLORS, a, st);
+    launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -270,7 +277,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = c->acc;
     a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w;
     pick_runs(g, &a.G, &a.runs_per_row);
-    be_launch_run(BE_RUN_INFER, a, st);
+    launch_run(BE_RUN_INFER, a, st);
     if (tm) cudaEventRecord(c->ev[3], st);
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
     be_launch_normalise(c->acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
@@ -319,7 +326,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
     a.g = g; a.cam = c->cam; a.NB = B;
     pick_runs(g, &a.G, &a.runs_per_row);
-    be_launch_run(BE_RUN_TRAINFWD, a, st);
+    launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
     BE_CUDA(cudaGetLastError());

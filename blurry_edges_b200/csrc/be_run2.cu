@@ -1,0 +1,348 @@
+// be_run2_kernel: the renderer + fused fold, second generation (replaces be_run_kernel of be_kernels.cu on the hot path).
+//
+// Same decomposition as before (one CTA walks a run of consecutive patches of a patch row; pixel slots (i, x mod R) keep an
+// image pixel on the same thread for every patch of the run that covers it; overlap sums are flushed with 16-byte vector
+// reductions when the pixel leaves the window) with three changes that the first ncu capture asked for
+// (profiles/r1a_run_kernel_full.txt: 28 % of warp time at CTA barriers, 2 CTAs/SM because of 96 registers/thread):
+//   * WARP SPECIALISATION: warps 0..6 render (2 slots per thread), warp 7 is the solver: it sums the warps' normal-equation
+//     partials, solves the 3x3 ridge system in fp64 and publishes the colours.  Producer/consumer hand-off uses named barriers
+//     (bar.arrive / bar.sync) instead of __syncthreads, so the render warps never wait for the solve of the patch they just
+//     finished: they run phase 1 of patch k, THEN phase 2 of patch k-1 (software pipeline, depth 1).
+//   * Per-slot state that must survive between the two phases (distances, soft indicators) and between patches (pixel values,
+//     the 15 overlap sums) lives in SHARED memory in thread-private slots (conflict-free float4 columns, no atomics, no
+//     barriers needed for it), which brings the kernel under 80 registers -> 3 CTAs (24 warps) per SM.
+//   * 8 warps per CTA balance the 4 SM sub-partitions (7 left one of them half empty).
+#include "be_internal.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NCOMP = BE_THREADS;            // 224 render threads (7 warps)
+constexpr int NTHR = NCOMP + 32;             // + solver warp
+constexpr int NSLOT = 2 * NCOMP;             // 448 slot columns in the shared arrays
+
+// named barriers with immediate ids (a register id would make ptxas reserve all 16):
+// 0 = __syncthreads, 1..2 = FULL[parity] (partials ready), 3..4 = DONE[parity] (colours ready)
+template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
+template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
+__device__ __forceinline__ void sync_full(int par) { if (par) bar_sync_id<2>(); else bar_sync_id<1>(); }
+__device__ __forceinline__ void arrive_full(int par) { if (par) bar_arrive_id<2>(); else bar_arrive_id<1>(); }
+__device__ __forceinline__ void sync_done(int par) { if (par) bar_sync_id<4>(); else bar_sync_id<3>(); }
+__device__ __forceinline__ void arrive_done(int par) { if (par) bar_arrive_id<4>(); else bar_arrive_id<3>(); }
+
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (hi ? v[i + 8] : v[i]) + __shfl_xor_sync(FULL, hi ? v[i] : v[i + 8], 16);
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (hi ? a[i + 4] : a[i]) + __shfl_xor_sync(FULL, hi ? a[i] : a[i + 4], 8);
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (hi ? b[i + 2] : b[i]) + __shfl_xor_sync(FULL, hi ? b[i] : b[i + 2], 4);
+    hi = lane & 2;
+    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(FULL, hi ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(FULL, d, 1);
+    return d;
+}
+
+__device__ __forceinline__ float ld_img(const BeImg& im, int b, int m, int c, int y, int x) {
+    return __ldg(im.p + b * im.sb + m * im.sm + c * im.sc + y * im.sy + x * im.sx);
+}
+
+// shared-memory plan (dynamic): all per-slot arrays are [.][NSLOT] columns of float4 -> consecutive lanes, consecutive 16 B
+template <int MODE>
+struct Smem {
+    static constexpr bool INFER = (MODE == BE_RUN_INFER), TRAIN = (MODE == BE_RUN_TRAINFWD);
+    static constexpr int NACC4 = INFER ? 4 : (TRAIN ? 2 : 0);   // float4 accumulators per slot
+    static constexpr int NST4 = (MODE == BE_RUN_COLORS) ? 0 : 2; // float4 stash words per slot and parity (d1,d2,h0,h1 | h2,h3,-,-)
+    static constexpr size_t off_pix = 0;                                            // float4 pix[2][NSLOT]
+    static constexpr size_t off_acc = off_pix + sizeof(float4) * 2 * NSLOT;         // float4 acc[NACC4][NSLOT]
+    static constexpr size_t off_st = off_acc + sizeof(float4) * NACC4 * NSLOT;      // float4 st[2 parities][NST4][NSLOT]
+    static constexpr size_t off_rec = off_st + sizeof(float4) * 2 * NST4 * NSLOT;   // float rec[4][BE_REC]
+    static constexpr size_t off_part = off_rec + sizeof(float) * 4 * BE_REC;        // float part[2][BE_WARPS][16]
+    static constexpr size_t off_col = off_part + sizeof(float) * 2 * BE_WARPS * 16; // float col[2][16]
+    static constexpr size_t off_axis = off_col + sizeof(float) * 2 * 16;            // float axis[24]
+    static constexpr size_t bytes = off_axis + sizeof(float) * 24;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
+    using SM = Smem<MODE>;
+    constexpr bool INFER = SM::INFER, TRAIN = SM::TRAIN, FOLD = INFER || TRAIN;
+    constexpr int NIMG = FOLD ? 2 : 1;
+    constexpr int ACCW = INFER ? BE_ACC : 8;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_pix = reinterpret_cast<float4*>(smem_raw + SM::off_pix);     // [2][NSLOT]: (p0r,p0g,p0b,p1r), (p1g,p1b,zgt,-)
+    float4* s_acc = reinterpret_cast<float4*>(smem_raw + SM::off_acc);     // [NACC4][NSLOT]
+    float4* s_st = reinterpret_cast<float4*>(smem_raw + SM::off_st);       // [2][NST4][NSLOT]
+    float* s_rec = reinterpret_cast<float*>(smem_raw + SM::off_rec);       // [4][BE_REC]
+    float* s_part = reinterpret_cast<float*>(smem_raw + SM::off_part);     // [2][BE_WARPS][16]
+    float* s_col = reinterpret_cast<float*>(smem_raw + SM::off_col);       // [2][16]: C[9], inv_refoc[2], z[2]
+    float* s_axis = reinterpret_cast<float*>(smem_raw + SM::off_axis);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const BeGeom g = a.g;
+    const int R = g.R, RR = R * R;
+
+    int blk = blockIdx.x;
+    const int run = blk % a.runs_per_row; blk /= a.runs_per_row;
+    const int py = blk % g.Hp;
+    const int b = blk / g.Hp;
+    const int px0 = run * a.G;
+    const int n = min(a.G, g.Wp - px0);
+    const int y0 = py * g.stride;
+    const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
+
+    if (tid < R) s_axis[tid] = be_axis(tid, R);
+    if (tid < 16 && (tid >> 3) < n)   // records of patches 0 and 1
+        reinterpret_cast<float4*>(s_rec)[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
+    __syncthreads();
+
+    if (warp == BE_WARPS) {
+        // ======================================= solver warp =======================================
+        for (int k = 0; k < n; ++k) {
+            const int par = k & 1;
+            float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 8 && k + 2 < n) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 2) * BE_REC) + lane);
+            sync_full(par);
+            float t = 0.0f;
+            if (lane < 16) {
+                const float* pp = s_part + (par * BE_WARPS) * 16 + lane;
+#pragma unroll
+                for (int wv = 0; wv < BE_WARPS; ++wv) t += pp[wv * 16];
+            }
+            float S[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) S[q] = __shfl_sync(FULL, t, q);
+            double Minv[6];
+            float C[9];
+            be_solve_colors(S, g.lam, Minv, C);
+            if (lane == 0) {
+                if (FOLD) {
+                    float* col = s_col + par * 16;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) col[q] = C[q];
+                    if (INFER) {
+                        const float* rec = s_rec + (k & 3) * BE_REC;
+                        const float z0 = rec[14], z1 = rec[15];
+                        const int cnt = (int)S[15];
+                        const float sg1 = (cnt & 1023) > 0 ? be_refocus_sigma(a.cam, z0) : BE_ETA_SHARP;   // blurry_edges_test.py:66-72
+                        const float sg2 = (cnt >> 10) > 0 ? be_refocus_sigma(a.cam, z1) : BE_ETA_SHARP;
+                        col[9] = 1.0f / (BE_SQRT2_F * sg1); col[10] = 1.0f / (BE_SQRT2_F * sg2);
+                        col[11] = z0; col[12] = z1;
+                    }
+                } else {
+                    // colours [NB][3(channel)][3(wedge)][Hp][Wp]  (blurry_edges_test.py:27 permute)
+                    float* dst = a.colors + (size_t)b * 9 * g.Hp * g.Wp + (size_t)py * g.Wp + px0 + k;
+#pragma unroll
+                    for (int wd = 0; wd < 3; ++wd)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dst[(size_t)(c * 3 + wd) * g.Hp * g.Wp] = C[3 * wd + c];
+                }
+            }
+            if (lane < 8 && k + 2 < n) reinterpret_cast<float4*>(s_rec + ((k + 2) & 3) * BE_REC)[lane] = nxt;
+            arrive_done(par);
+        }
+        return;
+    }
+
+    // ========================================= render warps =========================================
+    bool valid[2];
+    int si[2], j[2], j2[2];     // j: column cursor of phase 1 (patch k), j2: of phase 2 (patch k-1)
+    float Y[2];
+    unsigned mcount = 0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int slot = tid + s * NCOMP;
+        valid[s] = slot < RR;
+        si[s] = valid[s] ? slot / R : 0;
+        j[s] = valid[s] ? slot % R : 0;
+        j2[s] = j[s];
+        Y[s] = s_axis[si[s]];
+#pragma unroll
+        for (int q = 0; q < SM::NACC4; ++q) s_acc[q * NSLOT + slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid[s]) {
+            const int x = px0 * g.stride + j[s], y = y0 + si[s];
+            float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int m = 0; m < NIMG; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, b, m, c, y, x);
+            const float zg = TRAIN ? __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x) : 0.0f;
+            s_pix[slot] = make_float4(p[0], p[1], p[2], p[3]);
+            s_pix[NSLOT + slot] = make_float4(p[4], p[5], zg, 0.0f);
+        }
+    }
+    const float inv_sharp = 1.0f / (BE_SQRT2_F * BE_ETA_SHARP);
+
+    for (int k = 0; k <= n; ++k) {
+        // ---------------- phase 1 of patch k ----------------
+        if (k < n) {
+            const int par = k & 1;
+            BePatch P;
+            {
+                const float4* q4 = reinterpret_cast<const float4*>(s_rec + (k & 3) * BE_REC);
+                const float4 r0 = q4[0], r1 = q4[1], r2 = q4[2], r3 = q4[3], r4 = q4[4];
+                P.sn[0] = r0.x; P.sn[1] = r0.y; P.sn[2] = r0.z; P.sn[3] = r0.w;
+                P.cs[0] = r1.x; P.cs[1] = r1.y; P.cs[2] = r1.z; P.cs[3] = r1.w;
+                P.vx[0] = r2.x; P.vx[1] = r2.y; P.vy[0] = r2.z; P.vy[1] = r2.w;
+                P.flip[0] = r3.x; P.flip[1] = r3.y; P.z[0] = r3.z; P.z[1] = r3.w;
+                P.inv_eta[0] = r4.x; P.inv_eta[1] = r4.y; P.inv_eta[2] = r4.z; P.inv_eta[3] = r4.w;
+            }
+            float sums[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sums[q] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (valid[s]) {
+                    const int slot = tid + s * NCOMP;
+                    float d1, d2;
+                    be_pixel_dists(P, s_axis[j[s]], Y[s], g.w, &d1, &d2);
+                    const float4 pa = s_pix[slot], pb = s_pix[NSLOT + slot];
+                    const float pix[6] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y};
+                    float hh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int m = 0; m < NIMG; ++m) {
+                        const float h1 = be_h(d1, P.inv_eta[2 * m]), h2 = be_h(d2, P.inv_eta[2 * m + 1]);
+                        hh[2 * m] = h1; hh[2 * m + 1] = h2;
+                        float u[3];
+                        be_wedges(h1, h2, u);
+                        sums[0] = fmaf(u[0], u[0], sums[0]); sums[1] = fmaf(u[0], u[1], sums[1]); sums[2] = fmaf(u[0], u[2], sums[2]);
+                        sums[3] = fmaf(u[1], u[1], sums[3]); sums[4] = fmaf(u[1], u[2], sums[4]); sums[5] = fmaf(u[2], u[2], sums[5]);
+#pragma unroll
+                        for (int wd = 0; wd < 3; ++wd)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) sums[6 + 3 * wd + c] = fmaf(u[wd], pix[3 * m + c], sums[6 + 3 * wd + c]);
+                    }
+                    if (FOLD) {
+                        s_st[(par * SM::NST4 + 0) * NSLOT + slot] = make_float4(d1, d2, hh[0], hh[1]);
+                        s_st[(par * SM::NST4 + 1) * NSLOT + slot] = make_float4(hh[2], hh[3], 0.0f, 0.0f);
+                    }
+                    if (INFER) {
+                        const int mk = be_mask(d1, d2, a.densify_w != 0);
+                        sums[15] += (mk == 1) ? 1.0f : ((mk == 2) ? 1024.0f : 0.0f);   // two exact counters in one float
+                    }
+                    if (TRAIN) mcount += (be_mask(d1, d2, false) != 0 && pb.z != 0.0f) ? 1u : 0u;   // global_training.py:125-127
+                }
+            }
+            const float tot = warp_reduce16(sums, lane);
+            if (!(lane & 1)) s_part[(par * BE_WARPS + warp) * 16 + (lane >> 1)] = tot;
+            arrive_full(par);
+
+            // advance the phase-1 cursor: reload the pixel cache of slots whose image pixel changes
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int jn = j[s] - g.stride;
+                if (jn >= 0) { j[s] = jn; continue; }
+                j[s] = jn + R;
+                if (valid[s] && k + 1 < n) {
+                    const int slot = tid + s * NCOMP;
+                    const int x = (px0 + k + 1) * g.stride + j[s], y = y0 + si[s];
+                    float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int m = 0; m < NIMG; ++m)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, b, m, c, y, x);
+                    const float zg = TRAIN ? __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x) : 0.0f;
+                    s_pix[slot] = make_float4(p[0], p[1], p[2], p[3]);
+                    s_pix[NSLOT + slot] = make_float4(p[4], p[5], zg, 0.0f);
+                }
+            }
+        }
+
+        // ---------------- phase 2 of patch k-1 ----------------
+        if (k >= 1) {
+            const int kp = k - 1, par = kp & 1;
+            sync_done(par);
+            if (FOLD) {
+                const float* col = s_col + par * 16;
+                float C[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) C[q] = col[q];
+                const bool last = (kp + 1 == n);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (!valid[s]) continue;
+                    const int slot = tid + s * NCOMP;
+                    const int jc = j2[s];                                              // column of this slot in patch kp
+                    j2[s] = (jc - g.stride < 0) ? jc - g.stride + R : jc - g.stride;
+                    const float4 sa = s_st[(par * SM::NST4 + 0) * NSLOT + slot], sb = s_st[(par * SM::NST4 + 1) * NSLOT + slot];
+                    const float d1 = sa.x, d2 = sa.y;
+                    float4 acc0 = s_acc[slot], acc1 = s_acc[NSLOT + slot];
+                    float u[3], P1[3], P2[3];
+                    be_wedges(sa.z, sa.w, u);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) P1[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                    be_wedges(sb.x, sb.y, u);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) P2[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                    acc0.x += P1[0]; acc0.y += P1[1]; acc0.z += P1[2]; acc0.w += P2[0];
+                    acc1.x += P2[1]; acc1.y += P2[2];
+                    const float lb = be_boundary(d1, d2);                                    // blurry_edges_test.py:59-61
+                    const bool flush = last || (jc - g.stride < 0);
+                    float* dst = a.acc + (((size_t)b * g.H + y0 + si[s]) * g.W + (px0 + kp) * g.stride + jc) * ACCW;
+                    if (TRAIN) {
+                        acc1.z += lb;
+                        if (flush) {
+                            atomicAdd(reinterpret_cast<float4*>(dst), acc0);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + 1, acc1);
+                            acc0 = acc1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        s_acc[slot] = acc0; s_acc[NSLOT + slot] = acc1;
+                    }
+                    if (INFER) {
+                        float4 acc2 = s_acc[2 * NSLOT + slot], acc3 = s_acc[3 * NSLOT + slot];
+                        float Q[3];
+                        be_wedges(be_h(d1, inv_sharp), be_h(d2, inv_sharp), u);              // :63-64
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Q[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                        acc1.z += Q[0]; acc1.w += Q[1]; acc2.x += Q[2];
+                        be_wedges(be_h(d1, col[9]), be_h(d2, col[10]), u);                   // :73-74
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Q[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                        acc2.y += Q[0]; acc2.z += Q[1]; acc2.w += Q[2];
+                        const int mk = be_mask(d1, d2, a.densify_w != 0);                    // :47-57
+                        acc3.x += lb;
+                        acc3.y += (mk == 1) ? col[11] : ((mk == 2) ? col[12] : 0.0f);
+                        acc3.z += (mk > 0) ? 1.0f : 0.0f;
+                        if (flush) {
+                            atomicAdd(reinterpret_cast<float4*>(dst), acc0);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + 1, acc1);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + 2, acc2);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + 3, acc3);
+                            acc0 = acc1 = acc2 = acc3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        s_acc[slot] = acc0; s_acc[NSLOT + slot] = acc1; s_acc[2 * NSLOT + slot] = acc2; s_acc[3 * NSLOT + slot] = acc3;
+                    }
+                }
+            }
+        }
+    }
+    if (TRAIN) {
+        mcount = __reduce_add_sync(FULL, mcount);
+        if (lane == 0 && mcount) atomicAdd(a.mask_count, (unsigned long long)mcount);
+    }
+}
+
+}  // namespace
+
+template <int MODE>
+static void launch2(const BeRunArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(be_run2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<MODE>::bytes);
+        configured = true;
+    }
+    const int grid = a.NB * a.g.Hp * a.runs_per_row;
+    be_run2_kernel<MODE><<<grid, NTHR, Smem<MODE>::bytes, st>>>(a);
+}
+
+void be_launch_run2(int mode, const BeRunArgs& a, cudaStream_t st) {
+    if (mode == BE_RUN_INFER) launch2<BE_RUN_INFER>(a, st);
+    else if (mode == BE_RUN_TRAINFWD) launch2<BE_RUN_TRAINFWD>(a, st);
+    else launch2<BE_RUN_COLORS>(a, st);
+    ++g_be_launches;
+}
