@@ -7,5 +7,6 @@ from . import _lib
 from ._lib import BlurryEdgesError, Context, make_config
 from .fused import PostProcessFused
 from .losses import GlobalLossFused, LocalLossFused
+from .big import BigImageFused, block_windows, shard_blocks
 
-__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', '_lib']
+__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']

@@ -28,6 +28,10 @@ class BeImageLayout(C.Structure):
     _fields_ = [('sb', C.c_int64), ('sm', C.c_int64), ('sc', C.c_int64), ('sy', C.c_int64), ('sx', C.c_int64)]
 
 
+class BeBlock(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('img', 'oy', 'ox', 'py0', 'py1', 'px0', 'px1')]
+
+
 class BlurryEdgesError(RuntimeError):
     pass
 
@@ -49,6 +53,10 @@ _SIGS = {
     'be_colors_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, _P, _P]),
     'be_render_fold_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                      _P, _P, _P, _P, _P, _P, _P, _P]),
+    'be_colors_blocks_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.POINTER(BeBlock), C.c_int32, _P, _P]),
+    'be_render_fold_blocks': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.POINTER(BeBlock), C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, _P, _P]),
+    'be_fold_normalise': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
@@ -217,6 +225,41 @@ class Context:
                torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
         if want_thresholded:
             out.append(torch.empty(B, H, W, **kw))
+        return out
+
+    # ---- blocked (big-image) entry points --------------------------------------------------
+    @staticmethod
+    def _blocks(blocks):
+        arr = (BeBlock * len(blocks))()
+        for k, b in enumerate(blocks):
+            arr[k] = BeBlock(*[int(v) for v in b])
+        return arr
+
+    def colors_blocks(self, est, img, layout, blocks, param_mode=PARAMS_LOCAL10):
+        """est [nitem,L,10]; blocks = [(img, oy, ox, py0, py1, px0, px1)] per item -> colours [nitem,3,3,Hp,Wp]"""
+        n = est.shape[0]
+        out = torch.zeros(n, 3, 3, self.Hp, self.Wp, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.be_colors_blocks_fwd(self.h, _ptr(est), param_mode, _ptr(img), C.byref(layout), self._blocks(blocks), n,
+                                                _ptr(out), _stream(self.device)))
+        return out
+
+    def render_fold_blocks(self, est, img, layout, blocks, acc, densify_w=False, param_mode=PARAMS_RESTORED12):
+        """adds the blocks' pass-B sums into acc [*,accH,accW,16] (caller-zeroed)"""
+        with torch.cuda.device(self.device):
+            check(self.lib.be_render_fold_blocks(self.h, _ptr(est), param_mode, _ptr(img), C.byref(layout), self._blocks(blocks),
+                                                 est.shape[0], int(densify_w), acc.shape[-3], acc.shape[-2], _ptr(acc),
+                                                 _stream(self.device)))
+        return acc
+
+    def fold_normalise(self, acc, thres):
+        """acc [B,accH,accW,16] -> (image, sharp, refoc, bndry, depth, conf, depth_thresholded) at that size"""
+        B, H, W = acc.shape[0], acc.shape[1], acc.shape[2]
+        kw = dict(device=self.device, dtype=torch.float32)
+        out = [torch.empty(B, 2, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw),
+               torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
+        with torch.cuda.device(self.device):
+            check(self.lib.be_fold_normalise(self.h, _ptr(acc), B, H, W, float(thres), *[_ptr(t) for t in out], _stream(self.device)))
         return out
 
     # ---- training entry points -----------------------------------------------------------

@@ -51,6 +51,11 @@ struct be_ctx {
     float* st_out;
     size_t st_bytes;
     cudaStream_t st_stream;
+    // block descriptors of the blocked (big-image) entry points
+    BeBlock* blk_dev;
+    BeBlock* blk_pin;
+    int blk_cap;
+    cudaEvent_t blk_ev;
     // training workspace (lazily allocated by the loss entry points)
     float* gtable;      // [max_batch*L][BE_GREC]
     float* T;           // [max_batch][H][W][BE_TW]
@@ -185,6 +190,8 @@ int be_ctx_destroy(be_ctx* c) {
     cudaFree(c->table); cudaFree(c->acc);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
     cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials);
+    cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
+    if (c->blk_ev) cudaEventDestroy(c->blk_ev);
     if (c->st_stream) cudaStreamDestroy(c->st_stream);
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
@@ -247,7 +254,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     BeRunArgs a;
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
-    a.g = c->g; a.cam = c->cam; a.NB = M;
+    a.g = c->g; a.cam = c->cam; a.NB = M; a.accH = c->g.H; a.accW = c->g.W;
     pick_runs(c->g, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
@@ -275,7 +282,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     BeRunArgs a;
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = c->acc;
-    a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w;
+    a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
     pick_runs(g, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_INFER, a, st);
     if (tm) cudaEventRecord(c->ev[3], st);
@@ -324,7 +331,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.table = c->table; a.acc = c->acc;
     a.img.p = dev_img_ny; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
     a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
-    a.g = g; a.cam = c->cam; a.NB = B;
+    a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
     pick_runs(g, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
@@ -391,6 +398,97 @@ int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, cons
     a.kc = (float)sc.scale[0]; a.kbl = (float)(beta_bndry_loc * sc.scale[1]); a.ks = (float)(beta_smthns * sc.scale[2]);
     be_launch_loss(true, a, st);
     be_launch_loss_reduce(c->partials, B, sc, nullptr, dev_terms, dev_loss, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// blocked (big-image) entry points: blurry_edges_test_big.py:135-190 without the unfolded full_* tensors
+// ---------------------------------------------------------------------------------------------------
+static int upload_blocks(be_ctx* c, const be_block* host_blocks, int n, cudaStream_t st) {
+    if (n > c->blk_cap) {
+        if (c->blk_ev) BE_CUDA(cudaEventSynchronize(c->blk_ev));
+        cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
+        c->blk_dev = nullptr; c->blk_pin = nullptr; c->blk_cap = 0;
+        BE_CUDA(cudaMalloc(&c->blk_dev, (size_t)n * sizeof(BeBlock)));
+        BE_CUDA(cudaMallocHost(&c->blk_pin, (size_t)n * sizeof(BeBlock)));
+        c->blk_cap = n;
+    }
+    if (!c->blk_ev) BE_CUDA(cudaEventCreateWithFlags(&c->blk_ev, cudaEventDisableTiming));
+    else BE_CUDA(cudaEventSynchronize(c->blk_ev));        // the previous upload must have left the pinned buffer
+    const BeGeom& g = c->g;
+    for (int i = 0; i < n; ++i) {
+        const be_block& h = host_blocks[i];
+        BE_REQUIRE(h.py0 >= 0 && h.py1 <= g.Hp && h.px0 >= 0 && h.px1 <= g.Wp && h.py0 <= h.py1 && h.px0 <= h.px1,
+                   "block %d: patch window [%d,%d)x[%d,%d) outside the %dx%d patch grid", i, h.py0, h.py1, h.px0, h.px1, g.Hp, g.Wp);
+        BE_REQUIRE(h.oy >= 0 && h.ox >= 0 && h.img >= 0, "block %d: negative origin or image index", i);
+        BeBlock& d = c->blk_pin[i];
+        d.img = h.img; d.oy = h.oy; d.ox = h.ox; d.py0 = h.py0; d.py1 = h.py1; d.px0 = h.px0; d.px1 = h.px1; d.pad = 0;
+    }
+    BE_CUDA(cudaMemcpyAsync(c->blk_dev, c->blk_pin, (size_t)n * sizeof(BeBlock), cudaMemcpyHostToDevice, st));
+    BE_CUDA(cudaEventRecord(c->blk_ev, st));
+    return 0;
+}
+
+int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
+                         const be_block* blocks, int32_t nitem, float* dev_colors, void* stream) {
+    if (check_ctx(c) || check_layout(layout)) return 1;
+    if (nitem == 0) return 0;
+    BE_REQUIRE(dev_est && dev_img && dev_colors && blocks, "null pointer");
+    BE_REQUIRE(param_mode == BE_PARAMS_LOCAL10 || param_mode == BE_PARAMS_LOCALRAW10, "be_colors_blocks_fwd takes 10-parameter patches");
+    BE_REQUIRE(nitem > 0 && nitem <= 2 * c->cfg.max_batch, "nitem=%d exceeds 2*max_batch=%d", nitem, 2 * c->cfg.max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (upload_blocks(c, blocks, nitem, st)) return 1;
+    const int L = c->g.Hp * c->g.Wp;
+    be_launch_setup(dev_est, param_mode, nitem * L, c->cam, c->table, nullptr, st);
+    BeRunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors; a.blocks = c->blk_dev;
+    a.g = c->g; a.cam = c->cam; a.NB = nitem; a.accH = c->g.H; a.accW = c->g.W;
+    pick_runs(c->g, &a.G, &a.runs_per_row);
+    be_launch_run2(BE_RUN_COLORS, a, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
+                          const be_block* blocks, int32_t nblk, int32_t densify_w, int32_t acc_H, int32_t acc_W, float* dev_acc,
+                          void* stream) {
+    if (check_ctx(c) || check_layout(layout)) return 1;
+    if (nblk == 0) return 0;
+    BE_REQUIRE(dev_est && dev_img && dev_acc && blocks, "null pointer");
+    BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_render_fold_blocks takes 12-parameter patches");
+    BE_REQUIRE(nblk > 0 && nblk <= 2 * c->cfg.max_batch, "nblk=%d exceeds 2*max_batch=%d", nblk, 2 * c->cfg.max_batch);
+    const BeGeom& g = c->g;
+    for (int i = 0; i < nblk; ++i)
+        BE_REQUIRE(blocks[i].oy + g.H <= acc_H && blocks[i].ox + g.W <= acc_W, "block %d does not fit the %dx%d accumulator", i, acc_H, acc_W);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (upload_blocks(c, blocks, nblk, st)) return 1;
+    const int L = g.Hp * g.Wp;
+    be_launch_setup(dev_est, param_mode, nblk * L, c->cam, c->table, nullptr, st);
+    BeRunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc; a.blocks = c->blk_dev;
+    a.g = g; a.cam = c->cam; a.NB = nblk; a.densify_w = densify_w; a.accH = acc_H; a.accW = acc_W;
+    pick_runs(g, &a.G, &a.runs_per_row);
+    be_launch_run2(BE_RUN_INFER, a, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int be_fold_normalise(be_ctx* c, const float* dev_acc, int32_t B, int32_t acc_H, int32_t acc_W, double thres, float* dev_image,
+                      float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf, float* dev_depth_thr,
+                      void* stream) {
+    if (check_ctx(c)) return 1;
+    if (B == 0) return 0;
+    BE_REQUIRE(dev_acc && dev_image && dev_sharp && dev_refoc && dev_bndry && dev_depth && dev_conf, "null pointer");
+    BE_REQUIRE(acc_H >= c->g.R && acc_W >= c->g.R, "accumulator smaller than a patch");
+    BeGeom g = c->g;
+    g.H = acc_H; g.W = acc_W;
+    g.Hp = (acc_H - g.R) / g.stride + 1;
+    g.Wp = (acc_W - g.R) / g.stride + 1;
+    be_launch_normalise(dev_acc, g, B, (float)thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr,
+                        (cudaStream_t)stream);
     BE_CUDA(cudaGetLastError());
     return 0;
 }

@@ -25,6 +25,13 @@ struct BeImg {                        // strided view of an image tensor (elemen
     long long sb, sm, sc, sy, sx;
 };
 
+struct BeBlock {                      // one work item of a blocked (big-image) launch: a 147x147 block of a larger image
+    int img;                          // image / pair index used for pixel loads and for the accumulator
+    int oy, ox;                       // pixel origin of the block inside the larger image
+    int py0, py1, px0, px1;           // patch window of the block that is rendered (blurry_edges_test_big.py:166-177)
+    int pad;
+};
+
 struct BeRunArgs {
     const float* table;               // [NB*L][BE_REC] patch records (be_setup_kernel)
     BeImg img;
@@ -37,6 +44,8 @@ struct BeRunArgs {
     int NB;                           // pairs (INFER) or single images (COLORS)
     int G, runs_per_row;              // patches per CTA run, runs per patch row
     int densify_w;
+    const BeBlock* blocks;            // nullptr: item b is pair/image b at origin (0,0), all patches
+    int accH, accW;                   // accumulator plane size (= H, W unless blocked)
 };
 
 struct BeLossArgs {

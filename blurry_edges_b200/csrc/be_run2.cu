@@ -91,8 +91,15 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
     const int run = blk % a.runs_per_row; blk /= a.runs_per_row;
     const int py = blk % g.Hp;
     const int b = blk / g.Hp;
-    const int px0 = run * a.G;
-    const int n = min(a.G, g.Wp - px0);
+    int ib = b, oy = 0, ox = 0, pxlo = 0, pxhi = g.Wp;
+    if (a.blocks) {                   // blocked launch: item b is one block of a larger image
+        const BeBlock d = a.blocks[b];
+        if (py < d.py0 || py >= d.py1) return;
+        ib = d.img; oy = d.oy; ox = d.ox; pxlo = d.px0; pxhi = d.px1;
+    }
+    const int px0 = max(run * a.G, pxlo);
+    const int n = min(run * a.G + a.G, pxhi) - px0;
+    if (n <= 0) return;
     const int y0 = py * g.stride;
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
 
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
 #pragma unroll
             for (int m = 0; m < NIMG; ++m)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, b, m, c, y, x);
+                for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, ib, m, c, oy + y, ox + x);
             const float zg = TRAIN ? __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x) : 0.0f;
             s_pix[slot] = make_float4(p[0], p[1], p[2], p[3]);
             s_pix[NSLOT + slot] = make_float4(p[4], p[5], zg, 0.0f);
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
 #pragma unroll
                     for (int m = 0; m < NIMG; ++m)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, b, m, c, y, x);
+                        for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, ib, m, c, oy + y, ox + x);
                     const float zg = TRAIN ? __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x) : 0.0f;
                     s_pix[slot] = make_float4(p[0], p[1], p[2], p[3]);
                     s_pix[NSLOT + slot] = make_float4(p[4], p[5], zg, 0.0f);
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
                     acc1.x += P2[1]; acc1.y += P2[2];
                     const float lb = be_boundary(d1, d2);                                    // blurry_edges_test.py:59-61
                     const bool flush = last || (jc - g.stride < 0);
-                    float* dst = a.acc + (((size_t)b * g.H + y0 + si[s]) * g.W + (px0 + kp) * g.stride + jc) * ACCW;
+                    float* dst = a.acc + (((size_t)ib * a.accH + oy + y0 + si[s]) * a.accW + ox + (px0 + kp) * g.stride + jc) * ACCW;
                     if (TRAIN) {
                         acc1.z += lb;
                         if (flush) {

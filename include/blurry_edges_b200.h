@@ -93,6 +93,24 @@ int be_host_render_fold(be_ctx* ctx, const float* est, int32_t param_mode, const
                         float* image, float* sharp, float* refoc, float* bndry, float* depth, float* conf,
                         float* depth_thresholded);
 
+/* Blocked launches for images larger than the 147x147 network window (blurry_edges_test_big.py:113-190).  A block is a
+ * window of the larger image at pixel origin (oy, ox); only the patches [py0,py1) x [px0,px1) of its patch grid are
+ * rendered (the 10-patch margins are dropped except at the image border, :166-177).
+ * be_colors_blocks_fwd: pass A for nitem (block, image) items; est [nitem,L,10] -> colours [nitem,3,3,Hp,Wp].
+ * be_render_fold_blocks: pass B of nblk blocks (est [nblk,L,12]) ADDED into a caller-owned, caller-zeroed accumulator
+ *   [*,acc_H,acc_W,16] at the blocks' origins - the per-block patch grids are never stitched or unfolded.  Ranks of a
+ *   multi-GPU job render disjoint block subsets into their own accumulators and sum them (one reduce of 16 planes).
+ * be_fold_normalise: accumulator [B,acc_H,acc_W,16] -> the six maps (+ thresholded depth) at that size (:185-190). */
+typedef struct be_block { int32_t img, oy, ox, py0, py1, px0, px1; } be_block;
+int be_colors_blocks_fwd(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
+                         const be_image_layout* layout, const be_block* blocks, int32_t nitem, float* dev_colors, void* stream);
+int be_render_fold_blocks(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
+                          const be_image_layout* layout, const be_block* blocks, int32_t nblk, int32_t densify_w,
+                          int32_t acc_H, int32_t acc_W, float* dev_acc, void* stream);
+int be_fold_normalise(be_ctx* ctx, const float* dev_acc, int32_t B, int32_t acc_H, int32_t acc_W, double thres,
+                      float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf,
+                      float* dev_depth_thresholded, void* stream);
+
 /* GlobalLoss.forward + backward (global_training.py:62-157), in two stages so that a data-parallel caller can all-reduce
  * the depth-term normaliser between them (the depth term divides by the mask count of the WHOLE batch, :127).
  * Layouts are the dataset's (data/dataset.py:50-56): raw [B,L,12] network output, img_ny/img_gt [B,2,H,W,3],
