@@ -38,6 +38,10 @@ UNIT = 'patches/s'
 # algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
 # params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
 ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
+# dram__bytes_read.sum + dram__bytes_write.sum of be_run2_kernel<INFER> for one 64-pair launch, from the committed
+# `ncu --set full` capture profiles/r1b_run2_kernel_full.txt (155.3 MB + 37.9 MB); None for other batch sizes
+TRAFFIC_NCU_64 = 155.325440e6 + 37.926400e6
+TRAFFIC_NCU = None
 
 
 def peaks():
@@ -143,6 +147,79 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def _timed(fn, steps, warmup, dev, barrier, world):
+    """ms per call of fn (CUDA events on the current stream, max over ranks)."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def extra_configs(args, rank, world, dev, barrier):
+    """Secondary measurements of the other BASELINE.json configs (same JSON line, separate keys):
+    configs[2] global-loss training step fwd+bwd (4 pairs per GPU = batch 32 on 8 GPUs), configs[3] one 1027x1027 pair with
+    its 121 blocks sharded over the ranks, configs[4] densify 'w' with 32 pairs per GPU (256 on 8 GPUs)."""
+    import argparse as ap
+    import synth
+    from blurry_edges_b200 import BigImageFused, GlobalLossFused, PostProcessFused, shard_blocks
+    from oracle import be_oracle as O   # input synthesis only (restore_global)
+    import torch.distributed as dist
+    cam = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
+    base = dict(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=cam)
+    out = {}
+    steps = max(3, args.steps // 2)
+    # ---- configs[2]: training step of the loss (forward + analytic backward), data parallel -------------------------
+    Bt = 4
+    targs = ap.Namespace(batch_size=Bt, gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
+                         gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
+                         gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200], **base)
+    crit = GlobalLossFused(targs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
+    crit.update_gamma()
+    raw = synth.raw_global(Bt, L, seed=300 + rank).to(dev).requires_grad_(True)
+    img = synth.image_pairs(Bt, S, S, seed=301 + rank).to(dev)
+    gt, bd, deri, zg = [t.to(dev) for t in synth.loss_targets(Bt, S, S, seed=302 + rank)]
+
+    def train_step():
+        raw.grad = None
+        crit(raw, img, gt, bd, deri, zg).backward()
+
+    ms = _timed(train_step, steps, 3, dev, barrier, world)
+    out['train_step'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss, configs[2])', 'value': Bt * L * world / (ms / 1e3), 'unit': UNIT,
+                         'ms_per_step': ms, 'pairs_per_gpu': Bt, 'collective': '8-byte mask-count all-reduce between the two loss stages'}
+    # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
+    Bw = 32
+    pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
+    helper = PostProcessFused(pargs, None, dev, as_numpy=False)
+    est_w = O.restore_global(synth.raw_global(Bw, L, seed=310 + rank)).to(dev)
+    img_w = synth.image_pairs(Bw, S, S, seed=311 + rank).to(dev)
+    ms = _timed(lambda: helper(est_w, img_w, colors_only=False), steps, 3, dev, barrier, world)
+    out['dense_w'] = {'metric': "patches/sec pass B, --densify 'w' (configs[4])", 'value': Bw * L * world / (ms / 1e3), 'unit': UNIT,
+                      'ms_per_step': ms, 'pairs_per_gpu': Bw}
+    # ---- configs[3]: one 1027x1027 pair, 121 blocks sharded over the ranks ------------------------------------------
+    big = 1027
+    bargs = ap.Namespace(batch_size=1, big_img_size=[big, big], n_margin_patch=10, densify=None, **base)
+    bh = BigImageFused(bargs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
+    lo, hi = shard_blocks(bh.nblk, rank, world)
+    est_b = O.restore_global(synth.raw_global(hi - lo, L, seed=320 + rank)).to(dev)
+    big_img = (torch.from_numpy(synth.photon_pairs(1, big, big, seed=321)).float() / 190.0).permute(0, 1, 4, 2, 3)[0].contiguous().to(dev)
+    ms = _timed(lambda: bh(est_b, big_img), steps, 3, dev, barrier, world)
+    npatch_big = ((big - R) // STRIDE + 1) ** 2
+    out['big_1027'] = {'metric': 'patches/sec pass B + stitch + fold of one 1027x1027 pair (configs[3])', 'value': npatch_big / (ms / 1e3),
+                       'unit': UNIT, 'ms_per_image': ms, 'blocks': bh.nblk, 'blocks_this_rank': hi - lo, 'scaling': 'strong',
+                       'collective': 'sum-reduce of the [1027,1027,16] accumulator onto rank 0' if world > 1 else None}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from blurry_edges_b200 import Context, _lib, make_config
@@ -152,6 +229,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     B = args.pairs
+    global TRAFFIC_NCU
+    TRAFFIC_NCU = TRAFFIC_NCU_64 if B == 64 else None
     est_h, img_h = make_inputs(B, seed=100 + rank)
     est_h, img_h = est_h.pin_memory(), img_h.pin_memory()
     est, img = est_h.to(dev), img_h.to(dev)
@@ -200,6 +279,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    extra = {} if args.no_extra else extra_configs(args, rank, world, dev, barrier)
+
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -225,12 +306,13 @@ def run_ours(args, rank, world, local_rank):
                    'api': 'be_host_render_fold (pinned host buffers, synchronous)'},
            'gpu_launches': int(launches),
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                        'traffic': None, 'kernel': 'be_run_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
+                        'traffic': TRAFFIC_NCU, 'kernel': 'be_run2_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
                         'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
                         'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
                                 'see profiles/ for pipe utilisation'},
            'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run_kernel': shares[2], 'be_normalise_kernel': shares[3]},
            'clocks': clk.summary(), 'wall_s_timed_region': t_wall}
+    res.update(extra)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sec = time_cpu(args.ref_pairs, 2, cores)
@@ -260,6 +342,7 @@ def main():
     ap.add_argument('--pairs', type=int, default=64, help='image pairs per GPU per step (BASELINE configs[1]: 64)')
     ap.add_argument('--ref-pairs', type=int, default=4, help='pairs per step of the CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (train step, densify w, big image)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))

@@ -35,6 +35,8 @@ int fail(const char* fmt, ...) {
 
 }  // namespace
 
+constexpr int BE_HOST_CHUNKS = 8;   // pipeline depth of the host-buffer entry point
+
 struct be_ctx {
     be_config cfg;
     BeGeom g;
@@ -50,7 +52,8 @@ struct be_ctx {
     float* st_img;
     float* st_out;
     size_t st_bytes;
-    cudaStream_t st_stream;
+    cudaStream_t st_streams[3];
+    cudaEvent_t st_events[2 * BE_HOST_CHUNKS];
     // block descriptors of the blocked (big-image) entry points
     BeBlock* blk_dev;
     BeBlock* blk_pin;
@@ -192,7 +195,8 @@ int be_ctx_destroy(be_ctx* c) {
     cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials);
     cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
     if (c->blk_ev) cudaEventDestroy(c->blk_ev);
-    if (c->st_stream) cudaStreamDestroy(c->st_stream);
+    for (int i = 0; i < 3; ++i) if (c->st_streams[i]) cudaStreamDestroy(c->st_streams[i]);
+    for (int i = 0; i < 2 * BE_HOST_CHUNKS; ++i) if (c->st_events[i]) cudaEventDestroy(c->st_events[i]);
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     delete c;
     return 0;
@@ -499,38 +503,47 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
     if (check_ctx(c) || check_layout(layout)) return 1;
     if (B == 0) return 0;
     BE_REQUIRE(est && img && image && sharp && refoc && bndry && depth && conf, "null pointer");
-    BE_REQUIRE(B >= 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
-    if (B == 0) return 0;
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
+    BE_REQUIRE(layout->sb == 6LL * c->g.H * c->g.W, "host entry point needs pairs stored contiguously (layout.sb = 6*H*W)");
     const BeGeom& g = c->g;
     const size_t HW = (size_t)g.H * g.W, L = (size_t)g.Hp * g.Wp;
     const size_t mb = (size_t)c->cfg.max_batch;
     if (!c->st_est) {
-        BE_CUDA(cudaStreamCreateWithFlags(&c->st_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) BE_CUDA(cudaStreamCreateWithFlags(&c->st_streams[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 2 * BE_HOST_CHUNKS; ++i) BE_CUDA(cudaEventCreateWithFlags(&c->st_events[i], cudaEventDisableTiming));
         BE_CUDA(cudaMalloc(&c->st_est, mb * L * 12 * sizeof(float)));
         BE_CUDA(cudaMalloc(&c->st_img, mb * 6 * HW * sizeof(float)));
         BE_CUDA(cudaMalloc(&c->st_out, mb * 16 * HW * sizeof(float)));
         c->st_bytes = mb * (L * 12 + 22 * HW) * sizeof(float);
     }
-    cudaStream_t st = c->st_stream;
-    BE_CUDA(cudaMemcpyAsync(c->st_est, est, (size_t)B * L * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
-    BE_CUDA(cudaMemcpyAsync(c->st_img, img, (size_t)B * 6 * HW * sizeof(float), cudaMemcpyHostToDevice, st));
-    float* o = c->st_out;
-    float* d_image = o;                  float* d_sharp = o + (size_t)B * 6 * HW;
-    float* d_refoc = o + (size_t)B * 9 * HW;   float* d_bndry = o + (size_t)B * 12 * HW;
-    float* d_depth = o + (size_t)B * 13 * HW;  float* d_conf = o + (size_t)B * 14 * HW;
-    float* d_thr = o + (size_t)B * 15 * HW;
-    if (be_render_fold_fwd(c, c->st_est, param_mode, c->st_img, layout, B, densify_w, d_image, d_sharp, d_refoc, d_bndry,
-                           d_depth, d_conf, d_thr, (void*)st))
-        return 1;
+    // Software pipeline over chunks of pairs: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three streams, so that
+    // the PCIe transfers (the larger part of an end-to-end call) hide behind the renderer.
+    cudaStream_t s_in = c->st_streams[0], s_k = c->st_streams[1], s_out = c->st_streams[2];
+    const int nchunk = B < BE_HOST_CHUNKS ? B : BE_HOST_CHUNKS;
     const size_t f = sizeof(float);
-    BE_CUDA(cudaMemcpyAsync(image, d_image, (size_t)B * 6 * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaMemcpyAsync(sharp, d_sharp, (size_t)B * 3 * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaMemcpyAsync(refoc, d_refoc, (size_t)B * 3 * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaMemcpyAsync(bndry, d_bndry, (size_t)B * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaMemcpyAsync(depth, d_depth, (size_t)B * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaMemcpyAsync(conf, d_conf, (size_t)B * HW * f, cudaMemcpyDeviceToHost, st));
-    if (depth_thr) BE_CUDA(cudaMemcpyAsync(depth_thr, d_thr, (size_t)B * HW * f, cudaMemcpyDeviceToHost, st));
-    BE_CUDA(cudaStreamSynchronize(st));
+    float* o = c->st_out;
+    float* d_map[7] = {o, o + (size_t)B * 6 * HW, o + (size_t)B * 9 * HW, o + (size_t)B * 12 * HW, o + (size_t)B * 13 * HW,
+                       o + (size_t)B * 14 * HW, o + (size_t)B * 15 * HW};
+    float* h_map[7] = {image, sharp, refoc, bndry, depth, conf, depth_thr};
+    const size_t per[7] = {6 * HW, 3 * HW, 3 * HW, HW, HW, HW, HW};
+    for (int i = 0; i < nchunk; ++i) {
+        const int b0 = (int)((long long)B * i / nchunk), b1 = (int)((long long)B * (i + 1) / nchunk), nb = b1 - b0;
+        BE_CUDA(cudaMemcpyAsync(c->st_est + (size_t)b0 * L * 12, est + (size_t)b0 * L * 12, (size_t)nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->st_img + (size_t)b0 * 6 * HW, img + (size_t)b0 * 6 * HW, (size_t)nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaEventRecord(c->st_events[2 * i], s_in));
+        BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[2 * i], 0));
+        if (be_render_fold_fwd(c, c->st_est + (size_t)b0 * L * 12, param_mode, c->st_img + (size_t)b0 * 6 * HW, layout, nb, densify_w,
+                               d_map[0] + b0 * per[0], d_map[1] + b0 * per[1], d_map[2] + b0 * per[2], d_map[3] + b0 * per[3],
+                               d_map[4] + b0 * per[4], d_map[5] + b0 * per[5], d_map[6] + b0 * per[6], (void*)s_k))
+            return 1;
+        BE_CUDA(cudaEventRecord(c->st_events[2 * i + 1], s_k));
+        BE_CUDA(cudaStreamWaitEvent(s_out, c->st_events[2 * i + 1], 0));
+        for (int m = 0; m < 7; ++m) {
+            if (!h_map[m]) continue;
+            BE_CUDA(cudaMemcpyAsync(h_map[m] + b0 * per[m], d_map[m] + b0 * per[m], nb * per[m] * f, cudaMemcpyDeviceToHost, s_out));
+        }
+    }
+    BE_CUDA(cudaStreamSynchronize(s_out));
     return 0;
 }
 
