@@ -5,8 +5,9 @@ host-side mirror of the reference's helper classes.  Importing the package never
 any of its classes on a machine without the built library or without a CUDA device raises."""
 from . import _lib
 from ._lib import BlurryEdgesError, Context, make_config
+from .base import DepthEtas, PostProcessBase, PostProcessGlobalBase, PostProcessLocalBase
 from .fused import PostProcessFused
 from .losses import GlobalLossFused, LocalLossFused
 from .big import BigImageFused, block_windows, shard_blocks
 
-__all__ = ['BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']
+__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']

@@ -57,6 +57,21 @@ _SIGS = {
     'be_render_fold_blocks': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.POINTER(BeBlock), C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, _P, _P]),
     'be_fold_normalise': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'be_params2dists': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P]),
+    'be_params2dists_bwd': (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int64, _P, _P]),
+    'be_dists2indicators': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
+    'be_dists2indicators_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P]),
+    'be_elementwise': (C.c_int, [_P, C.c_int32, _P, C.c_double, C.c_int64, _P, _P]),
+    'be_elementwise_bwd': (C.c_int, [_P, C.c_int32, _P, _P, C.c_double, C.c_int64, _P, _P]),
+    'be_etas2depth': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    'be_etas2depth_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    'be_inverse_3by3': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    'be_inverse_3by3_bwd': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    'be_image_derivative': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    'be_image_derivative_bwd': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    'be_fold': (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    'be_fold_depth': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    'be_unfold': (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
@@ -226,6 +241,13 @@ class Context:
         if want_thresholded:
             out.append(torch.empty(B, H, W, **kw))
         return out
+
+    def call(self, name, *args):
+        """Generic launcher for the method-granularity entry points: tensors become device pointers, the current
+        stream is appended."""
+        conv = [(_ptr(a) if a.dtype == torch.float32 else C.c_void_p(a.data_ptr())) if isinstance(a, torch.Tensor) else a for a in args]
+        with torch.cuda.device(self.device):
+            check(getattr(self.lib, name)(self.h, *conv, _stream(self.device)))
 
     # ---- blocked (big-image) entry points --------------------------------------------------
     @staticmethod

@@ -135,11 +135,17 @@ void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) {
     if (v == 1) be_launch_run(mode, a, st); else be_launch_run2(mode, a, st);
 }
 
-int pick_runs(const BeGeom& g, int* G, int* runs) {
-    // one CTA per patch row unless the row is very long (big images): then chunks of <= 96 patches
-    const int maxG = 96;
-    *runs = (g.Wp + maxG - 1) / maxG;
-    *G = (g.Wp + *runs - 1) / *runs;
+// Split every patch row into `runs` runs of G consecutive patches (one CTA each).  Long runs amortise the sliding-window
+// state (pixel loads, accumulator flushes) best; small batches need shorter runs to fill the 148 SMs (3 CTAs each) a few
+// times over.  Runs never get shorter than 8 patches, never longer than 96.
+int pick_runs(const BeGeom& g, int items, int* G, int* runs) {
+    const int maxG = 96, minG = 8, target_ctas = 148 * 3 * 3;
+    int r = (g.Wp + maxG - 1) / maxG;
+    const long long rows = (long long)items * g.Hp;
+    while ((long long)r * rows < target_ctas && (g.Wp + r) / (r + 1) >= minG) ++r;
+    *runs = r;
+    *G = (g.Wp + r - 1) / r;
+    *runs = (g.Wp + *G - 1) / *G;
     return 0;
 }
 
@@ -259,7 +265,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
     a.g = c->g; a.cam = c->cam; a.NB = M; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, &a.G, &a.runs_per_row);
+    pick_runs(c->g, M, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -287,7 +293,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = c->acc;
     a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, &a.G, &a.runs_per_row);
+    pick_runs(g, B, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_INFER, a, st);
     if (tm) cudaEventRecord(c->ev[3], st);
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
@@ -304,8 +310,7 @@ static int ensure_train_ws(be_ctx* c) {
     if (c->gtable) return 0;
     const BeGeom& g = c->g;
     const size_t mb = (size_t)c->cfg.max_batch, L = (size_t)g.Hp * g.Wp;
-    int G, runs;
-    pick_runs(g, &G, &runs);
+    const int runs = (g.Wp + 7) / 8;   // worst case of pick_runs
     const size_t b1 = mb * L * BE_GREC * sizeof(float), b2 = mb * g.H * g.W * BE_TW * sizeof(float);
     const size_t b3 = mb * g.Hp * runs * 8 * sizeof(float);
     BE_CUDA(cudaMalloc(&c->gtable, b1));
@@ -336,7 +341,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.img.p = dev_img_ny; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
     a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
     a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, &a.G, &a.runs_per_row);
+    pick_runs(g, B, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
@@ -360,7 +365,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     a.table = c->table; a.gtable = c->gtable; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
     a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
     a.g = g; a.NB = B;
-    pick_runs(g, &a.G, &a.runs_per_row);
+    pick_runs(g, B, &a.G, &a.runs_per_row);
     BeLossScale sc;
     memset(&sc, 0, sizeof(sc));
     sc.nterms = 7;
@@ -449,7 +454,7 @@ int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, co
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors; a.blocks = c->blk_dev;
     a.g = c->g; a.cam = c->cam; a.NB = nitem; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, &a.G, &a.runs_per_row);
+    pick_runs(c->g, nitem, &a.G, &a.runs_per_row);
     be_launch_run2(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -474,7 +479,7 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc; a.blocks = c->blk_dev;
     a.g = g; a.cam = c->cam; a.NB = nblk; a.densify_w = densify_w; a.accH = acc_H; a.accW = acc_W;
-    pick_runs(g, &a.G, &a.runs_per_row);
+    pick_runs(g, nblk, &a.G, &a.runs_per_row);
     be_launch_run2(BE_RUN_INFER, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -493,6 +498,120 @@ int be_fold_normalise(be_ctx* c, const float* dev_acc, int32_t B, int32_t acc_H,
     g.Wp = (acc_W - g.R) / g.stride + 1;
     be_launch_normalise(dev_acc, g, B, (float)thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr,
                         (cudaStream_t)stream);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// method-granularity entry points (the reference's helper-class METHODS, reference layouts)
+// ---------------------------------------------------------------------------------------------------
+#define BE_OP_PROLOGUE(...)                 \
+    if (check_ctx(c)) return 1;             \
+    if (n_ == 0) return 0;                  \
+    BE_REQUIRE(__VA_ARGS__, "null pointer"); \
+    cudaStream_t st = (cudaStream_t)stream;
+
+int be_params2dists(be_ctx* c, const float* dev_params, int32_t K, int32_t B, int64_t Lsp, float* dev_dists, void* stream) {
+    const int64_t n_ = (int64_t)B * Lsp;
+    BE_OP_PROLOGUE(dev_params && dev_dists)
+    BE_REQUIRE(K >= 8 && Lsp >= 1, "params need >= 8 channels");
+    be_op_params2dists(dev_params, K, B, (size_t)Lsp, c->g.R, c->g.w, dev_dists, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_params2dists_bwd(be_ctx* c, const float* dev_params, int32_t K, const float* dev_grad_dists, int32_t B, int64_t Lsp,
+                        float* dev_grad_params, void* stream) {
+    const int64_t n_ = (int64_t)B * Lsp;
+    BE_OP_PROLOGUE(dev_params && dev_grad_dists && dev_grad_params)
+    be_op_params2dists_bwd(dev_params, K, dev_grad_dists, B, (size_t)Lsp, c->g.R, c->g.w, dev_grad_params, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_dists2indicators(be_ctx* c, const float* dev_dists, const float* dev_etas, int32_t B, int64_t Lsp, float* dev_wedges, void* stream) {
+    const int64_t n_ = (int64_t)B * Lsp;
+    BE_OP_PROLOGUE(dev_dists && dev_etas && dev_wedges)
+    be_op_indicators(dev_dists, dev_etas, B, (size_t)Lsp, c->g.R * c->g.R, dev_wedges, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_dists2indicators_bwd(be_ctx* c, const float* dev_dists, const float* dev_etas, const float* dev_grad_wedges, int32_t B, int64_t Lsp,
+                            float* dev_grad_dists, float* dev_grad_etas, void* stream) {
+    const int64_t n_ = (int64_t)B * Lsp;
+    BE_OP_PROLOGUE(dev_dists && dev_etas && dev_grad_wedges && dev_grad_dists && dev_grad_etas)
+    be_op_indicators_bwd(dev_dists, dev_etas, dev_grad_wedges, B, (size_t)Lsp, c->g.R * c->g.R, dev_grad_dists, dev_grad_etas, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_elementwise(be_ctx* c, int32_t op, const float* dev_x, double p0, int64_t n_, float* dev_y, void* stream) {
+    BE_OP_PROLOGUE(dev_x && dev_y)
+    BE_REQUIRE(op >= 0 && op <= 2, "unknown elementwise op %d", op);
+    be_op_unary(op, dev_x, (float)p0, c->cam, (size_t)n_, dev_y, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_elementwise_bwd(be_ctx* c, int32_t op, const float* dev_x, const float* dev_grad_y, double p0, int64_t n_, float* dev_grad_x,
+                       void* stream) {
+    BE_OP_PROLOGUE(dev_x && dev_grad_y && dev_grad_x)
+    BE_REQUIRE(op >= 0 && op <= 2, "unknown elementwise op %d", op);
+    be_op_unary_bwd(op, dev_x, dev_grad_y, (float)p0, c->cam, (size_t)n_, dev_grad_x, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_etas2depth(be_ctx* c, const float* dev_eta1, const float* dev_eta2, int64_t n_, float* dev_z, void* stream) {
+    BE_OP_PROLOGUE(dev_eta1 && dev_eta2 && dev_z)
+    be_op_depth(dev_eta1, dev_eta2, c->cam, (size_t)n_, dev_z, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_etas2depth_bwd(be_ctx* c, const float* dev_eta1, const float* dev_eta2, const float* dev_grad_z, int64_t n_, float* dev_g1,
+                      float* dev_g2, void* stream) {
+    BE_OP_PROLOGUE(dev_eta1 && dev_eta2 && dev_grad_z && dev_g1 && dev_g2)
+    be_op_depth_bwd(dev_eta1, dev_eta2, dev_grad_z, c->cam, (size_t)n_, dev_g1, dev_g2, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_inverse_3by3(be_ctx* c, const float* dev_A, int64_t n_, float* dev_inv, void* stream) {
+    BE_OP_PROLOGUE(dev_A && dev_inv)
+    be_op_inverse3(dev_A, (size_t)n_, dev_inv, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_inverse_3by3_bwd(be_ctx* c, const float* dev_inv, const float* dev_grad_inv, int64_t n_, float* dev_grad_A, void* stream) {
+    BE_OP_PROLOGUE(dev_inv && dev_grad_inv && dev_grad_A)
+    be_op_inverse3_bwd(dev_inv, dev_grad_inv, (size_t)n_, dev_grad_A, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_image_derivative(be_ctx* c, const float* dev_img, int64_t n_, int32_t H, int32_t W, float* dev_out, void* stream) {
+    BE_OP_PROLOGUE(dev_img && dev_out)
+    BE_REQUIRE(H >= 3 && W >= 3, "image smaller than the 3x3 Sobel kernel");
+    be_op_sobel(dev_img, (size_t)n_, H, W, dev_out, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_image_derivative_bwd(be_ctx* c, const float* dev_img, const float* dev_grad_out, int64_t n_, int32_t H, int32_t W,
+                            float* dev_grad_img, void* stream) {
+    BE_OP_PROLOGUE(dev_img && dev_grad_out && dev_grad_img)
+    be_op_sobel_bwd(dev_img, dev_grad_out, (size_t)n_, H, W, dev_grad_img, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_fold(be_ctx* c, const float* dev_patches, int64_t n_, int32_t mode, float* dev_out, void* stream) {
+    BE_OP_PROLOGUE(dev_patches && dev_out)
+    be_op_fold(dev_patches, (size_t)n_, c->g, mode, dev_out, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_fold_depth(be_ctx* c, const float* dev_depth_map, const int32_t* dev_depth_mask, int64_t n_, float* dev_depth, float* dev_conf,
+                  void* stream) {
+    BE_OP_PROLOGUE(dev_depth_map && dev_depth_mask && dev_depth && dev_conf)
+    be_op_fold_depth(dev_depth_map, dev_depth_mask, (size_t)n_, c->g, dev_depth, dev_conf, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_unfold(be_ctx* c, const float* dev_img, int64_t n_, int32_t mode, float* dev_patches, void* stream) {
+    BE_OP_PROLOGUE(dev_img && dev_patches)
+    be_op_unfold(dev_img, (size_t)n_, c->g, mode, dev_patches, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }

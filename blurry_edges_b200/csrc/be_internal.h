@@ -85,3 +85,21 @@ void be_launch_refold(const float* unfolded, const BeGeom& g, int M, float* imag
 void be_launch_cover_count(const BeGeom& g, float* out, cudaStream_t st);
 
 extern long long g_be_launches;
+
+// method-granularity ops (be_ops.cu)
+void be_op_params2dists(const float* params, int K, int B, size_t Lsp, int R, float w, float* dists, cudaStream_t st);
+void be_op_params2dists_bwd(const float* params, int K, const float* gd, int B, size_t Lsp, int R, float w, float* gp, cudaStream_t st);
+void be_op_indicators(const float* dists, const float* etas, int B, size_t Lsp, int RR, float* wedges, cudaStream_t st);
+void be_op_indicators_bwd(const float* dists, const float* etas, const float* gw, int B, size_t Lsp, int RR, float* gd, float* ge,
+                          cudaStream_t st);
+void be_op_unary(int op, const float* x, float p0, const BeCam& cam, size_t n, float* y, cudaStream_t st);
+void be_op_unary_bwd(int op, const float* x, const float* gy, float p0, const BeCam& cam, size_t n, float* gx, cudaStream_t st);
+void be_op_depth(const float* e1, const float* e2, const BeCam& cam, size_t n, float* z, cudaStream_t st);
+void be_op_depth_bwd(const float* e1, const float* e2, const float* gz, const BeCam& cam, size_t n, float* g1, float* g2, cudaStream_t st);
+void be_op_inverse3(const float* A, size_t n, float* out, cudaStream_t st);
+void be_op_inverse3_bwd(const float* inv, const float* g, size_t n, float* gA, cudaStream_t st);
+void be_op_sobel(const float* img, size_t N, int H, int W, float* out, cudaStream_t st);
+void be_op_sobel_bwd(const float* img, const float* gout, size_t N, int H, int W, float* gimg, cudaStream_t st);
+void be_op_fold(const float* patches, size_t P, const BeGeom& g, int mode, float* out, cudaStream_t st);
+void be_op_fold_depth(const float* dmap, const int* dmask, size_t B, const BeGeom& g, float* depth, float* conf, cudaStream_t st);
+void be_op_unfold(const float* img, size_t P, const BeGeom& g, int mode, float* patches, cudaStream_t st);

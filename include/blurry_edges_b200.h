@@ -134,6 +134,42 @@ int be_local_loss(be_ctx* ctx, const float* dev_est, const float* dev_img_ny, co
                   const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, float* dev_terms, float* dev_loss,
                   float* dev_grad, void* stream);
 
+/* Method-granularity entry points: one per METHOD of PostProcessBase / PostProcessGlobalBase / DepthEtas, on the
+ * reference's own tensor layouts, each with its backward (autograd of the reference).  Lsp = Hp*Wp for the global layout
+ * ([B,K,Hp,Wp], [B,2,R,R,Hp,Wp], ...) and 1 for the local layout ([B,K], [B,2,R,R], ...).  The fused entry points above
+ * never call these; they exist so that subclasses written against the reference's base classes run on this library.
+ *   be_params2dists        utils/postprocessing_loss.py:43-86   params [B,K>=8,Lsp] (first 8 channels) -> dists [B,2,R,R,Lsp]
+ *   be_dists2indicators    :91-95     dists [B,2,R,R,Lsp], etas [B,2,Lsp] -> wedges [B,3,R,R,Lsp]
+ *   be_elementwise         op 0 params2etas :88-89, op 1 normalized_gaussian(x, delta=p0) :97-98,
+ *                          op 2 DepthEtas.depth2sigma(depth, rho_prime=p0) utils/depth_etas.py:36-37
+ *   be_etas2depth          utils/depth_etas.py:23-34
+ *   be_inverse_3by3        :104-112   n matrices [n,3,3]
+ *   be_image_derivative    :114-117   n planes [n,H,W] -> [n,H-2,W-2]
+ *   be_fold                :151-164   n planes of patches [n,R,R,Hp,Wp] -> [n,H,W]; mode 0 divides by num_patches, 1 = plain sum
+ *   be_fold_depth          :166-173   depth_map fp32 + depth_mask int32 [n,R,R,Hp,Wp] -> depth, confidence [n,H,W]
+ *   be_unfold              nn.Unfold  n planes [n,H,W] -> [n,R,R,Hp,Wp]; mode 0 = adjoint of be_fold mode 0, 1 = plain */
+int be_params2dists(be_ctx* ctx, const float* dev_params, int32_t K, int32_t B, int64_t Lsp, float* dev_dists, void* stream);
+int be_params2dists_bwd(be_ctx* ctx, const float* dev_params, int32_t K, const float* dev_grad_dists, int32_t B, int64_t Lsp,
+                        float* dev_grad_params, void* stream);
+int be_dists2indicators(be_ctx* ctx, const float* dev_dists, const float* dev_etas, int32_t B, int64_t Lsp, float* dev_wedges, void* stream);
+int be_dists2indicators_bwd(be_ctx* ctx, const float* dev_dists, const float* dev_etas, const float* dev_grad_wedges, int32_t B,
+                            int64_t Lsp, float* dev_grad_dists, float* dev_grad_etas, void* stream);
+int be_elementwise(be_ctx* ctx, int32_t op, const float* dev_x, double p0, int64_t n, float* dev_y, void* stream);
+int be_elementwise_bwd(be_ctx* ctx, int32_t op, const float* dev_x, const float* dev_grad_y, double p0, int64_t n, float* dev_grad_x,
+                       void* stream);
+int be_etas2depth(be_ctx* ctx, const float* dev_eta1, const float* dev_eta2, int64_t n, float* dev_z, void* stream);
+int be_etas2depth_bwd(be_ctx* ctx, const float* dev_eta1, const float* dev_eta2, const float* dev_grad_z, int64_t n, float* dev_g1,
+                      float* dev_g2, void* stream);
+int be_inverse_3by3(be_ctx* ctx, const float* dev_A, int64_t n, float* dev_inv, void* stream);
+int be_inverse_3by3_bwd(be_ctx* ctx, const float* dev_inv, const float* dev_grad_inv, int64_t n, float* dev_grad_A, void* stream);
+int be_image_derivative(be_ctx* ctx, const float* dev_img, int64_t n, int32_t H, int32_t W, float* dev_out, void* stream);
+int be_image_derivative_bwd(be_ctx* ctx, const float* dev_img, const float* dev_grad_out, int64_t n, int32_t H, int32_t W,
+                            float* dev_grad_img, void* stream);
+int be_fold(be_ctx* ctx, const float* dev_patches, int64_t n, int32_t mode, float* dev_out, void* stream);
+int be_fold_depth(be_ctx* ctx, const float* dev_depth_map, const int32_t* dev_depth_mask, int64_t n, float* dev_depth, float* dev_conf,
+                  void* stream);
+int be_unfold(be_ctx* ctx, const float* dev_img, int64_t n, int32_t mode, float* dev_patches, void* stream);
+
 /* Measurement hook: with timing enabled, be_render_fold_fwd brackets each of its four device operations with CUDA
  * events on the caller's stream; be_ctx_last_timing waits for the last call and returns their durations in ms:
  * ms4 = {accumulator memset, be_setup_kernel, be_run_kernel, be_normalise_kernel}. */
