@@ -109,8 +109,8 @@ class BigImageFused(nn.Module):
         if self.process_group is None:
             return self.finish(self.render_partial(est, big_img), thres)
         import torch.distributed as dist
+        from .dist_utils import reduce_accumulator
         rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
         lo, hi = shard_blocks(self.nblk, rank, world)
-        acc = self.render_partial(est, big_img, lo, hi)
-        dist.reduce(acc, dst=dist.get_global_rank(self.process_group, 0), group=self.process_group)
+        acc = reduce_accumulator(self.render_partial(est, big_img, lo, hi), self.process_group)
         return self.finish(acc, thres) if rank == 0 else None

@@ -100,9 +100,8 @@ class GlobalLossFused(nn.Module):
         gimg, gbnd, cnt = self.ctx.global_loss_stage1(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self._f32(bndry_depth))
         npatch = B * L
         if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(cnt, group=self.process_group)      # depth normaliser over the WHOLE batch (global_training.py:127)
-            npatch *= dist.get_world_size(self.process_group)
+            from .dist_utils import sync_loss_normalisers
+            cnt, npatch = sync_loss_normalisers(cnt, npatch, self.process_group)   # normalisers of the WHOLE batch
         terms, loss, grad = self.ctx.global_loss_stage2(B, self.gammas(), npatch, cnt, want_grad)
         self.global_image, self.global_bndry, self.terms, self.mask_count = gimg, gbnd, terms, cnt
         if want_grad:

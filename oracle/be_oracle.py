@@ -351,7 +351,7 @@ def restore_global(raw: torch.Tensor) -> torch.Tensor:
 
 def global_loss(raw: torch.Tensor, img_ny: torch.Tensor, img_gt: torch.Tensor, bndry_dist: torch.Tensor,
                 deri: torch.Tensor, bndry_depth: torch.Tensor, gammas, g: Geometry, cam: Camera,
-                trace_form: bool = False, return_terms: bool = False):
+                trace_form: bool = False, return_terms: bool = False, global_batch: int | None = None, mask_sum=None):
     """global_training.py:93-157.  raw [B,L,12] network output, img_* [B,2,H,W,3],
     bndry_dist/bndry_depth [B,H,W], deri [B,2,H-2,W-2,3]; gammas = (color, color_cons,
     bndry_cons, smthns, smthns_cons, bndry_loc, depth)."""
@@ -379,14 +379,18 @@ def global_loss(raw: torch.Tensor, img_ny: torch.Tensor, img_gt: torch.Tensor, b
     zero = torch.zeros((), dtype=dt)
     dmap = torch.where(m == 1, r['z1'].view(-1, 1, 1), torch.where(m == 2, r['z2'].view(-1, 1, 1), zero))
     msk = ((zg_p != 0) & (m != 0)).to(dt)
+    # `global_batch` / `mask_sum`: this call holds one rank's slice of a larger batch; the means then run over the
+    # GLOBAL batch (data-parallel recipe of DESIGN.md section 6) so that the ranks' terms simply add up.
+    scale = 1.0 if global_batch is None else B / global_batch
+    msum = msk.sum() if mask_sum is None else torch.as_tensor(mask_sum, dtype=dt)
     terms = torch.stack([
-        ((gt_p - P) ** 2).sum(2).mean(),
-        ((P - gi_p) ** 2).sum(2).mean(),
-        ((lb - gb_p) ** 2).mean(),
-        ((Pd - dgt_p) ** 2).sum(2).mean(),
-        ((Pd - dgi_p) ** 2).sum(2).mean(),
-        ((bd_p * lb) ** 2).mean(),
-        (((dmap - zg_p) * msk) ** 2).sum() / msk.sum()])
+        ((gt_p - P) ** 2).sum(2).mean() * scale,
+        ((P - gi_p) ** 2).sum(2).mean() * scale,
+        ((lb - gb_p) ** 2).mean() * scale,
+        ((Pd - dgt_p) ** 2).sum(2).mean() * scale,
+        ((Pd - dgi_p) ** 2).sum(2).mean() * scale,
+        ((bd_p * lb) ** 2).mean() * scale,
+        (((dmap - zg_p) * msk) ** 2).sum() / msum])
     loss = (torch.as_tensor(gammas, dtype=dt) * terms).sum()
     if return_terms:
         return loss, terms, dict(gimg=gimg.reshape(B, 2, 3, g.H, g.W), gbnd=gbnd, msum=msk.sum())
