@@ -6,8 +6,8 @@ any of its classes on a machine without the built library or without a CUDA devi
 from . import _lib
 from ._lib import BlurryEdgesError, Context, make_config
 from .base import DepthEtas, PostProcessBase, PostProcessGlobalBase, PostProcessLocalBase
-from .fused import PostProcessFused
+from .fused import PostProcessFused, PostProcessLocalFused
 from .losses import GlobalLossFused, LocalLossFused
 from .big import BigImageFused, block_windows, shard_blocks
 
-__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']
+__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']

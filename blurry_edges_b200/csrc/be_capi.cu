@@ -151,6 +151,14 @@ int pick_runs(const BeGeom& g, int items, int* G, int* runs) {
 
 }  // namespace
 
+static int ensure_acc(be_ctx* c) {
+    if (c->acc) return 0;
+    const size_t bytes = (size_t)c->cfg.max_batch * c->g.H * c->g.W * BE_ACC * sizeof(float);
+    BE_CUDA(cudaMalloc(&c->acc, bytes));
+    c->acc_bytes = bytes;
+    return 0;
+}
+
 extern "C" {
 
 int be_abi_version(void) { return BE_ABI_VERSION; }
@@ -176,11 +184,10 @@ int be_ctx_create(be_ctx** out, const be_config* cfg) {
 
     const size_t L = (size_t)g.Hp * g.Wp;
     c->table_bytes = 2 * (size_t)cfg->max_batch * L * BE_REC * sizeof(float);
-    c->acc_bytes = (size_t)cfg->max_batch * g.H * g.W * BE_ACC * sizeof(float);
-    if (cudaMalloc(&c->table, c->table_bytes) != cudaSuccess || cudaMalloc(&c->acc, c->acc_bytes) != cudaSuccess) {
-        cudaFree(c->table);
+    c->acc_bytes = 0;                                    // the fold accumulator is allocated by the first entry point that folds
+    if (cudaMalloc(&c->table, c->table_bytes) != cudaSuccess) {
         delete c;
-        return fail("cudaMalloc of the %.1f MiB workspace failed", (c->table_bytes + c->acc_bytes) / 1048576.0);
+        return fail("cudaMalloc of the %.1f MiB patch-record table failed", c->table_bytes / 1048576.0);
     }
     *out = c;
     return 0;
@@ -280,6 +287,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_render_fold_fwd takes 12-parameter patches");
     BE_REQUIRE(B >= 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
     if (B == 0) return 0;
+    if (ensure_acc(c)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     const BeGeom& g = c->g;
     const int L = g.Hp * g.Wp;
@@ -307,6 +315,7 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
 // training entry points
 // ---------------------------------------------------------------------------------------------------
 static int ensure_train_ws(be_ctx* c) {
+    if (ensure_acc(c)) return 1;
     if (c->gtable) return 0;
     const BeGeom& g = c->g;
     const size_t mb = (size_t)c->cfg.max_batch, L = (size_t)g.Hp * g.Wp;

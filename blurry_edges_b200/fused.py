@@ -105,3 +105,33 @@ class PostProcessFused(nn.Module):
         if self.as_numpy:
             return tuple(m.detach().cpu().numpy() for m in maps)       # blurry_edges_test.py:100
         return tuple(maps)
+
+
+class PostProcessLocalFused(nn.Module):
+    """Drop-in for `global_data_pre_cal.PostProcess(args, device)` (global_data_pre_cal.py:35-50): pass A on a flat batch of
+    patches.  forward(params [N,10], pat_ny [N,R,R,3]) -> colours [N,3(channel),3(wedge)]."""
+
+    def __init__(self, args, device='cuda:0'):
+        super().__init__()
+        self.device = torch.device(device)
+        self.R, self.w, self.batch_size = int(args.R), float(args.w), int(args.batch_size)
+        self._geo = dict(R=self.R, stride=1, H=self.R, W=self.R, w=self.w, alpha_lambda=float(args.alpha_lambda),
+                         cam=dict(args.cam_params), mag=float(args.mag))
+        self.ctx = None
+        self.lambda_ridge = (float(args.alpha_lambda) * self.R ** 2) ** 2
+
+    def get_colors(self, params, pat_ny):
+        N, R = params.shape[0], self.R
+        if params.dim() != 2 or params.shape[1] != 10 or tuple(pat_ny.shape) != (N, R, R, 3):
+            raise _lib.BlurryEdgesError(f'expects params [N,10] and pat_ny [N,{R},{R},3], got {tuple(params.shape)}, {tuple(pat_ny.shape)}')
+        if self.ctx is None or 2 * self.ctx.max_batch < N:
+            if self.ctx is not None:
+                self.ctx.close()
+            self.ctx = _lib.Context(_lib.make_config(max_batch=(N + 1) // 2, **self._geo), self.device)
+        est = params.to(device=self.device, dtype=torch.float32).reshape(N, 1, 10).contiguous()
+        pat = pat_ny.to(device=self.device, dtype=torch.float32).contiguous()
+        lay = _lib.BeImageLayout(3 * R * R, 0, 1, 3 * R, 3)
+        return self.ctx.colors(est, pat, lay, _lib.PARAMS_LOCAL10).view(N, 3, 3)
+
+    def forward(self, params, pat_ny):
+        return self.get_colors(params, pat_ny)

@@ -183,3 +183,18 @@ def test_errors_are_loud():
     with pytest.raises(BlurryEdgesError):
         ctx.render_fold(torch.cat([est, est]).cuda(), torch.cat([img, img]).cuda(), _lib.planar_layout(S, S))  # B > max_batch
     assert len(ctx.render_fold(est[:0].cuda(), img[:0].cuda(), _lib.planar_layout(S, S))) == 7   # empty batch is a no-op
+
+
+def test_precal_local_colors_vs_oracle_and_golden():
+    """global_data_pre_cal.PostProcess equivalent: flat batch of patches, [N,R,R,3] pixels."""
+    import argparse
+    from blurry_edges_b200 import PostProcessLocalFused
+    g = geom(147)
+    est = synth.est_local(1, 40, seed=21)[0]
+    pat = synth.image_pairs(40, 21, 21, seed=22)[:, 0]
+    args = argparse.Namespace(R=21, w=1.0, alpha_lambda=5e-3, batch_size=1, mag=4.0,
+                              cam_params={'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6})
+    col = PostProcessLocalFused(args, 'cuda:0')(est.cuda(), pat.cuda()).cpu().numpy()
+    assert col.shape == (40, 3, 3)
+    assert relmax(col, O.colors_local(est.to(F64), pat.to(F64), g).numpy()) < 1e-5
+    assert relmax(col, Golden('inference')('precal/f64')) < 1e-5
