@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BeGeom g = a.g;
-    const int R = g.R, RR = R * R;
+    const int R = g.R;
 
     int blk = blockIdx.x;
     const int run = blk % a.runs_per_row; blk /= a.runs_per_row;
@@ -163,10 +163,17 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
     unsigned mcount = 0;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        const int slot = tid + s * NCOMP;
-        valid[s] = slot < RR;
-        si[s] = valid[s] ? slot / R : 0;
-        j[s] = valid[s] ? slot % R : 0;
+        // Slot -> pixel mapping: warp w owns `rpw` consecutive column residues (3 for R=21), lanes run over the R rows of a
+        // residue.  A slot's pixel changes (reload + flush) when its residue's column wraps, so with all slots of a warp
+        // sharing <= 3 residues the reload/flush code is executed by a warp in ~1 of 5 patches instead of in every patch
+        // (with lanes spread over all residues some lane wrapped every time: 16 % of all issued instructions, ncu r1b).
+        const int slot = tid + s * NCOMP;              // index into the thread-private shared arrays
+        const int rpw = (R + BE_WARPS - 1) / BE_WARPS;
+        const int u = lane + 32 * s;
+        const int res = warp * rpw + u / R;
+        valid[s] = (u < rpw * R) && (res < R);
+        si[s] = valid[s] ? u % R : 0;
+        j[s] = valid[s] ? res : 0;
         j2[s] = j[s];
         Y[s] = s_axis[si[s]];
 #pragma unroll
