@@ -231,15 +231,16 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) sums[6 + 3 * wd + c] = fmaf(u[wd], pix[3 * m + c], sums[6 + 3 * wd + c]);
                     }
-                    if (FOLD) {
-                        s_st[(par * SM::NST4 + 0) * NSLOT + slot] = make_float4(d1, d2, hh[0], hh[1]);
-                        s_st[(par * SM::NST4 + 1) * NSLOT + slot] = make_float4(hh[2], hh[3], 0.0f, 0.0f);
-                    }
+                    int mk = 0;
                     if (INFER) {
-                        const int mk = be_mask(d1, d2, a.densify_w != 0);
+                        mk = be_mask(d1, d2, a.densify_w != 0);
                         sums[15] += (mk == 1) ? 1.0f : ((mk == 2) ? 1024.0f : 0.0f);   // two exact counters in one float
                     }
                     if (TRAIN) mcount += (be_mask(d1, d2, false) != 0 && pb.z != 0.0f) ? 1u : 0u;   // global_training.py:125-127
+                    if (FOLD) {
+                        s_st[(par * SM::NST4 + 0) * NSLOT + slot] = make_float4(d1, d2, hh[0], hh[1]);
+                        s_st[(par * SM::NST4 + 1) * NSLOT + slot] = make_float4(hh[2], hh[3], __int_as_float(mk), 0.0f);
+                    }
                 }
             }
             const float tot = warp_reduce16(sums, lane);
@@ -273,9 +274,10 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
             sync_done(par);
             if (FOLD) {
                 const float* col = s_col + par * 16;
-                float C[9];
+                // P_c = sum_w u_w C[w][c] with u0 = 1 - u1 - u2:  C0 + u1 (C1 - C0) + u2 (C2 - C0)
+                float C0[3], D1[3], D2[3];
 #pragma unroll
-                for (int q = 0; q < 9; ++q) C[q] = col[q];
+                for (int c = 0; c < 3; ++c) { C0[c] = col[c]; D1[c] = col[3 + c] - col[c]; D2[c] = col[6 + c] - col[c]; }
                 const bool last = (kp + 1 == n);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -286,13 +288,17 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
                     const float4 sa = s_st[(par * SM::NST4 + 0) * NSLOT + slot], sb = s_st[(par * SM::NST4 + 1) * NSLOT + slot];
                     const float d1 = sa.x, d2 = sa.y;
                     float4 acc0 = s_acc[slot], acc1 = s_acc[NSLOT + slot];
-                    float u[3], P1[3], P2[3];
-                    be_wedges(sa.z, sa.w, u);
+                    float P1[3], P2[3];
+                    {
+                        const float u1 = sa.z * (1.0f - sa.w), u2 = sa.w;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) P1[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
-                    be_wedges(sb.x, sb.y, u);
+                        for (int c = 0; c < 3; ++c) P1[c] = fmaf(u1, D1[c], fmaf(u2, D2[c], C0[c]));
+                    }
+                    {
+                        const float u1 = sb.x * (1.0f - sb.y), u2 = sb.y;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) P2[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                        for (int c = 0; c < 3; ++c) P2[c] = fmaf(u1, D1[c], fmaf(u2, D2[c], C0[c]));
+                    }
                     acc0.x += P1[0]; acc0.y += P1[1]; acc0.z += P1[2]; acc0.w += P2[0];
                     acc1.x += P2[1]; acc1.y += P2[2];
                     const float lb = be_boundary(d1, d2);                                    // blurry_edges_test.py:59-61
@@ -310,15 +316,25 @@ __global__ void __launch_bounds__(NTHR, 3) be_run2_kernel(const BeRunArgs a) {
                     if (INFER) {
                         float4 acc2 = s_acc[2 * NSLOT + slot], acc3 = s_acc[3 * NSLOT + slot];
                         float Q[3];
-                        be_wedges(be_h(d1, inv_sharp), be_h(d2, inv_sharp), u);              // :63-64
+                        {   // eta = 1e-4 render (:63-64): |d| >= 4*sqrt2*1e-4 saturates erf to +-1 exactly in fp32, which is the
+                            // case for every pixel of most warps -> warp-uniform fast path with identical results
+                            float h1, h2;
+                            const bool near = fabsf(d1) < 4.0f * BE_SQRT2_F * BE_ETA_SHARP || fabsf(d2) < 4.0f * BE_SQRT2_F * BE_ETA_SHARP;
+                            if (__any_sync(__activemask(), near)) { h1 = be_h(d1, inv_sharp); h2 = be_h(d2, inv_sharp); }
+                            else { h1 = (d1 > 0.0f) ? 1.0f : 0.0f; h2 = (d2 > 0.0f) ? 1.0f : 0.0f; }
+                            const float u1 = h1 * (1.0f - h2);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) Q[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                            for (int c = 0; c < 3; ++c) Q[c] = fmaf(u1, D1[c], fmaf(h2, D2[c], C0[c]));
+                        }
                         acc1.z += Q[0]; acc1.w += Q[1]; acc2.x += Q[2];
-                        be_wedges(be_h(d1, col[9]), be_h(d2, col[10]), u);                   // :73-74
+                        {   // refocused render (:73-74)
+                            const float h1 = be_h(d1, col[9]), h2 = be_h(d2, col[10]);
+                            const float u1 = h1 * (1.0f - h2);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) Q[c] = fmaf(u[0], C[c], fmaf(u[1], C[3 + c], u[2] * C[6 + c]));
+                            for (int c = 0; c < 3; ++c) Q[c] = fmaf(u1, D1[c], fmaf(h2, D2[c], C0[c]));
+                        }
                         acc2.y += Q[0]; acc2.z += Q[1]; acc2.w += Q[2];
-                        const int mk = be_mask(d1, d2, a.densify_w != 0);                    // :47-57
+                        const int mk = __float_as_int(sb.z);                                 // :47-57, computed in phase 1
                         acc3.x += lb;
                         acc3.y += (mk == 1) ? col[11] : ((mk == 2) ? col[12] : 0.0f);
                         acc3.z += (mk > 0) ? 1.0f : 0.0f;
