@@ -20,6 +20,10 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int T_NY = 0, T_GT = 6, T_GI = 12, T_GB = 18, T_BD = 19, T_ZG = 20, T_DGT = 24, T_DGI = 30;
 
+// T is stored as BE_TW/4 planes of float4 per pixel ([9][B*H*W] float4): the threads of a warp own neighbouring pixels, so a
+// 16-byte load of one plane touches ~half the sectors of a record-major layout, and every fetched sector is fully used.
+__device__ __forceinline__ size_t t_off(size_t plane_stride, size_t pix, int k) { return (size_t)(k >> 2) * plane_stride + pix * 4 + (k & 3); }
+
 __device__ __forceinline__ int cover_1d(int y, int R, int s, int np) {
     const int hi = min(y / s, np - 1);
     const int lo = (y - R + 1 <= 0) ? 0 : (y - R + s) / s;
@@ -56,10 +60,10 @@ __global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __
     const float4 q0 = src[0], q1 = src[1];
     const float n = (float)(cover_1d(y, g.R, g.stride, g.Hp) * cover_1d(x, g.R, g.stride, g.Wp));
     const float v[7] = {q0.x / n, q0.y / n, q0.z / n, q0.w / n, q1.x / n, q1.y / n, q1.z / n};
-    float* t = T + idx * BE_TW;
+    const size_t PS = (size_t)B * HW * 4;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) t[T_GI + c] = v[c];
-    t[T_GB] = v[6];
+    for (int c = 0; c < 6; ++c) T[t_off(PS, idx, T_GI + c)] = v[c];
+    T[t_off(PS, idx, T_GB)] = v[6];
     if (gimg) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) gimg[((size_t)b * 6 + c) * HW + p] = v[c];
@@ -76,18 +80,18 @@ __global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, con
     if (idx >= (size_t)B * HW) return;
     const size_t p = idx % HW;
     const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
-    float* t = T + idx * BE_TW;
+    const size_t PS = (size_t)B * HW * 4;
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const size_t o = (((size_t)b * 2 + m) * HW + p) * 3 + c;          // dataset-native [B,2,H,W,3]
-            t[T_NY + 3 * m + c] = img_ny[o];
-            t[T_GT + 3 * m + c] = img_gt[o];
+            T[t_off(PS, idx, T_NY + 3 * m + c)] = img_ny[o];
+            T[t_off(PS, idx, T_GT + 3 * m + c)] = img_gt[o];
         }
-    t[T_BD] = log2f(bndry_dist[idx] + 1.0f);                                  // global_training.py:118
-    t[T_ZG] = bndry_depth[idx];
-    t[21] = t[22] = t[23] = 0.0f;
+    T[t_off(PS, idx, T_BD)] = log2f(bndry_dist[idx] + 1.0f);                  // global_training.py:118
+    T[t_off(PS, idx, T_ZG)] = bndry_depth[idx];
+    T[t_off(PS, idx, 21)] = T[t_off(PS, idx, 22)] = T[t_off(PS, idx, 23)] = 0.0f;
     const bool interior = (y >= 1 && y < g.H - 1 && x >= 1 && x < g.W - 1);
 #pragma unroll
     for (int mc = 0; mc < 6; ++mc) {
@@ -96,15 +100,15 @@ __global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, con
             const int m = mc / 3, c = mc % 3;
             dgt = deri[((((size_t)b * 2 + m) * (g.H - 2) + (y - 1)) * (g.W - 2) + (x - 1)) * 3 + c];
             // Sobel magnitude of the (already normalised) global image, utils/postprocessing_loss.py:114-117
-            const float* q = T + idx * BE_TW + T_GI + mc;
-            const long long rs = (long long)g.W * BE_TW, cs = BE_TW;
+            const float* q = T + t_off(PS, idx, T_GI + mc);
+            const long long rs = (long long)g.W * 4, cs = 4;
             const float a = q[-rs - cs], bb = q[-rs], cc = q[-rs + cs], d = q[-cs], f = q[cs], gg = q[rs - cs], hh = q[rs], ii = q[rs + cs];
             const float sx = (cc - a) + 2.0f * (f - d) + (ii - gg);
             const float sy = (a + 2.0f * bb + cc) - (gg + 2.0f * hh + ii);
             dgi = sqrtf(sx * sx + sy * sy + 1e-8f);
         }
-        t[T_DGT + mc] = dgt;
-        t[T_DGI + mc] = dgi;
+        T[t_off(PS, idx, T_DGT + mc)] = dgt;
+        T[t_off(PS, idx, T_DGI + mc)] = dgi;
     }
 }
 
@@ -169,6 +173,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
     const float Y[2] = {s_axis[sl[0].i], s_axis[sl[1].i]};
     const float X[2] = {s_axis[sl[0].j], s_axis[sl[1].j]};
     const float kd = LOCAL ? 0.0f : a.gamma_d / (float)(*a.mask_count);
+    const size_t TPS = (size_t)a.NB * g.H * g.W * 4;      // floats between consecutive float4 planes of T
 
     float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
@@ -194,14 +199,14 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
         const float* tp[2];
 #pragma unroll
         for (int s = 0; s < 2; ++s)
-            tp[s] = LOCAL ? nullptr : a.T + (((size_t)b * g.H + y0 + sl[s].i) * g.W + x0 + sl[s].j) * BE_TW;
+            tp[s] = LOCAL ? nullptr : a.T + (((size_t)b * g.H + y0 + sl[s].i) * g.W + x0 + sl[s].j) * 4;   // plane 0 of this pixel
         auto ld_ny = [&](int s, float* y) {
             if (LOCAL) {
                 const float* p = a.l_ny + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
                 y[0] = __ldg(p); y[1] = __ldg(p + 1); y[2] = __ldg(p + 2);
             } else {
                 const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
-                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + 4));
+                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS));
                 y[0] = q0.x; y[1] = q0.y; y[2] = q0.z; y[3] = q0.w; y[4] = q1.x; y[5] = q1.y;
             }
         };
@@ -293,10 +298,10 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                     }
                     bdv[s] = __ldg(a.l_bd + ((size_t)b * R + sl[s].i) * R + sl[s].j);
                 } else {
-                    const float2 t1 = __ldg(reinterpret_cast<const float2*>(tp[s] + 6));
-                    const float4 t2 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8));
-                    const float4 t3 = __ldg(reinterpret_cast<const float4*>(tp[s] + 12));
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp[s] + 16));
+                    const float2 t1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS + 2));
+                    const float4 t2 = __ldg(reinterpret_cast<const float4*>(tp[s] + 2 * TPS));
+                    const float4 t3 = __ldg(reinterpret_cast<const float4*>(tp[s] + 3 * TPS));
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp[s] + 4 * TPS));
                     const float gt[6] = {t1.x, t1.y, t2.x, t2.y, t2.z, t2.w};
                     const float gi[6] = {t3.x, t3.y, t3.z, t3.w, t4.x, t4.y};
                     gbv[s] = t4.z; bdv[s] = t4.w;
@@ -339,9 +344,9 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                     const float* p = a.l_deri + (((size_t)b * (R - 2) + sl[s].i - 1) * (R - 2) + sl[s].j - 1) * 3;
                     dgt[0] = __ldg(p); dgt[1] = __ldg(p + 1); dgt[2] = __ldg(p + 2);
                 } else {
-                    const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 24));
-                    const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 28));
-                    const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 32));
+                    const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
+                    const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
+                    const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
                     dgt[0] = t6.x; dgt[1] = t6.y; dgt[2] = t6.z; dgt[3] = t6.w; dgt[4] = t7.x; dgt[5] = t7.y;
                     dgi[0] = t7.z; dgi[1] = t7.w; dgi[2] = t8.x; dgi[3] = t8.y; dgi[4] = t8.z; dgi[5] = t8.w;
                 }
@@ -478,7 +483,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                         const float e = lb - gbv[s];
                         lossacc[2] = fmaf(e, e, lossacc[2]);
                         glb = fmaf(2.0f * a.kbc, e, glb);
-                        const float zgv = __ldg(tp[s] + T_ZG);
+                        const float zgv = __ldg(tp[s] + 5 * TPS);
                         const int mk = be_mask(d1[s], d2[s], false);
                         if (zgv != 0.0f && mk != 0) {
                             const float e2 = ((mk == 1) ? P.z[0] : P.z[1]) - zgv;
