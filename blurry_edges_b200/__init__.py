@@ -7,7 +7,8 @@ from . import _lib
 from ._lib import BlurryEdgesError, Context, make_config
 from .base import DepthEtas, PostProcessBase, PostProcessGlobalBase, PostProcessLocalBase
 from .fused import PostProcessFused, PostProcessLocalFused
+from .pipeline import DepthEstimatorFused
 from .losses import GlobalLossFused, LocalLossFused
 from .big import BigImageFused, block_windows, shard_blocks
 
-__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'block_windows', 'shard_blocks', '_lib']
+__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'DepthEstimatorFused', 'block_windows', 'shard_blocks', '_lib']

@@ -72,6 +72,9 @@ _SIGS = {
     'be_fold': (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     'be_fold_depth': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     'be_unfold': (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    'be_patch_gather': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    'be_assemble_pm': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    'be_eval_depth': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
@@ -245,6 +248,9 @@ class Context:
     def call(self, name, *args):
         """Generic launcher for the method-granularity entry points: tensors become device pointers, the current
         stream is appended."""
+        for a in args:
+            if isinstance(a, torch.Tensor) and not (a.is_cuda and a.is_contiguous()):
+                raise BlurryEdgesError('expected contiguous CUDA tensors')
         conv = [(_ptr(a) if a.dtype == torch.float32 else C.c_void_p(a.data_ptr())) if isinstance(a, torch.Tensor) else a for a in args]
         with torch.cuda.device(self.device):
             check(getattr(self.lib, name)(self.h, *conv, _stream(self.device)))

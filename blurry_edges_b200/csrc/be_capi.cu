@@ -625,6 +625,28 @@ int be_unfold(be_ctx* c, const float* dev_img, int64_t n_, int32_t mode, float* 
     return 0;
 }
 
+int be_patch_gather(be_ctx* c, const float* dev_img, int64_t n_, float* dev_vec, void* stream) {
+    BE_OP_PROLOGUE(dev_img && dev_vec)
+    be_op_patch_gather(dev_img, (size_t)n_, c->g, dev_vec, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_assemble_pm(be_ctx* c, const float* dev_params, const float* dev_colors, int64_t n_, float* dev_pm, void* stream) {
+    BE_OP_PROLOGUE(dev_params && dev_colors && dev_pm)
+    be_op_assemble_pm(dev_params, dev_colors, (size_t)n_, (size_t)c->g.Hp * c->g.Wp, dev_pm, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_eval_depth(be_ctx* c, const float* dev_depth, const float* dev_gt, int64_t n_, int32_t H, int32_t W, int32_t crop, double* dev_sums6,
+                  void* stream) {
+    BE_OP_PROLOGUE(dev_depth && dev_gt && dev_sums6)
+    BE_REQUIRE(crop >= 0 && 2 * crop < H && 2 * crop < W, "crop %d too large for %dx%d", crop, H, W);
+    BE_CUDA(cudaMemsetAsync(dev_sums6, 0, (size_t)n_ * 6 * sizeof(double), st));
+    be_op_eval_depth(dev_depth, dev_gt, (size_t)n_, H, W, crop, dev_sums6, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const float* img, const be_image_layout* layout,
                         int32_t B, int32_t densify_w, float* image, float* sharp, float* refoc, float* bndry, float* depth,
                         float* conf, float* depth_thr) {

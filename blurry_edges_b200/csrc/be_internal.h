@@ -103,3 +103,6 @@ void be_op_sobel_bwd(const float* img, const float* gout, size_t N, int H, int W
 void be_op_fold(const float* patches, size_t P, const BeGeom& g, int mode, float* out, cudaStream_t st);
 void be_op_fold_depth(const float* dmap, const int* dmask, size_t B, const BeGeom& g, float* depth, float* conf, cudaStream_t st);
 void be_op_unfold(const float* img, size_t P, const BeGeom& g, int mode, float* patches, cudaStream_t st);
+void be_op_patch_gather(const float* img, size_t M, const BeGeom& g, float* vec, cudaStream_t st);
+void be_op_assemble_pm(const float* params, const float* colors, size_t B, size_t L, float* pm, cudaStream_t st);
+void be_op_eval_depth(const float* pred, const float* gt, size_t N, int H, int W, int crop, double* out6, cudaStream_t st);

@@ -346,3 +346,84 @@ void be_op_fold_depth(const float* dmap, const int* dmask, size_t B, const BeGeo
 void be_op_unfold(const float* img, size_t P, const BeGeom& g, int mode, float* patches, cudaStream_t st) {
     k_unfold<<<blocks_for(P * g.R * g.R * g.Hp * g.Wp), TPB, 0, st>>>(img, P, g, mode, patches); ++g_be_launches;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Glue of the inference driver (blurry_edges_test.py:119-138), SURVEY.md section 8f rank 1
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// image [M,3,H,W] -> vec [M*Hp*Wp, 3, R, R]  (nn.Unfold + permute(0,4,5,1,2,3).reshape of :119-121 in one pass)
+__global__ void __launch_bounds__(TPB) k_patch_gather(const float* __restrict__ img, size_t M, BeGeom g, float* __restrict__ vec) {
+    const size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+    const size_t per = (size_t)3 * g.R * g.R;
+    if (idx >= M * g.Hp * g.Wp * per) return;
+    const int j = (int)(idx % g.R), i = (int)((idx / g.R) % g.R), c = (int)((idx / ((size_t)g.R * g.R)) % 3);
+    const size_t n = idx / per;
+    const int px = (int)(n % g.Wp), py = (int)((n / g.Wp) % g.Hp);
+    const size_t m = n / ((size_t)g.Wp * g.Hp);
+    vec[idx] = __ldg(img + ((m * 3 + c) * g.H + py * g.stride + i) * g.W + px * g.stride + j);
+}
+
+// params [2,L,10] (raw LocalStage output) + colours [2,3,3,Hp,Wp] -> pm [1,L,38] (:123-132):
+// per image (xy/3, (wrap(angles)-pi)/pi, eta_coef-0.5, (colours-0.5)*2), the two images concatenated per patch
+__global__ void __launch_bounds__(TPB) k_assemble_pm(const float* __restrict__ params, const float* __restrict__ colors, size_t B, size_t L,
+                                                     float* __restrict__ pm) {
+    const size_t idx = (size_t)blockIdx.x * TPB + threadIdx.x;
+    if (idx >= B * L * 38) return;
+    const int k = (int)(idx % 38);
+    const size_t l = (idx / 38) % L, b = idx / (38 * L);
+    const int m = k / 19, q = k % 19;
+    const size_t item = b * 2 + m;
+    float v;
+    if (q < 10) {
+        const float p = __ldg(params + (item * L + l) * 10 + q);
+        if (q < 4) v = p / 3.0f;
+        else if (q < 8) v = (be_wrap_2pi(p) - BE_PI_F) / BE_PI_F;
+        else v = p - 0.5f;
+    } else {
+        v = (__ldg(colors + (item * 9 + (q - 10)) * L + l) - 0.5f) * 2.0f;      // colours [item][c*3+w][l]
+    }
+    pm[idx] = v;
+}
+
+// eval_depth (utils/metrics.py:3-21) partial sums per image: n, #acc<tau, #acc<tau^2, #acc<tau^3, sum err^2, sum err/gt
+__global__ void __launch_bounds__(TPB) k_eval_depth(const float* __restrict__ pred, const float* __restrict__ gt, int H, int W, int crop,
+                                                    float z_min, float z_max, float tau, double* __restrict__ out6) {
+    __shared__ double sh[TPB][6];
+    const size_t img = blockIdx.y;
+    const int Hc = H - 2 * crop, Wc = W - 2 * crop;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t t = (size_t)blockIdx.x * TPB + threadIdx.x; t < (size_t)Hc * Wc; t += (size_t)gridDim.x * TPB) {
+        const int y = (int)(t / Wc) + crop, x = (int)(t % Wc) + crop;
+        const float raw = pred[(img * H + y) * W + x], gv = gt[(img * H + y) * W + x];
+        if (!(raw > 0.0f)) continue;                                         // error_mask = depth_map > 0 (blurry_edges_test.py:148)
+        const float p = fminf(fmaxf(raw, z_min), z_max);
+        const float err = fabsf(gv - p);
+        const float pn = fminf(fmaxf((p - z_min) / (z_max - z_min), 0.0f), 1.0f), gn = fminf(fmaxf((gv - z_min) / (z_max - z_min), 0.0f), 1.0f);
+        const float acc = fmaxf(gn / (pn + 1e-8f), pn / (gn + 1e-8f));
+        a[0] += 1.0; a[1] += acc < tau; a[2] += acc < tau * tau; a[3] += acc < tau * tau * tau;
+        a[4] += (double)err * err; a[5] += (double)err / gv;
+    }
+    for (int k = 0; k < 6; ++k) sh[threadIdx.x][k] = a[k];
+    __syncthreads();
+    for (int off = TPB / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off)
+            for (int k = 0; k < 6; ++k) sh[threadIdx.x][k] += sh[threadIdx.x + off][k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 6; ++k) atomicAdd(out6 + img * 6 + k, sh[0][k]);
+}
+
+}  // namespace
+
+void be_op_patch_gather(const float* img, size_t M, const BeGeom& g, float* vec, cudaStream_t st) {
+    k_patch_gather<<<blocks_for(M * g.Hp * g.Wp * 3 * g.R * g.R), TPB, 0, st>>>(img, M, g, vec); ++g_be_launches;
+}
+void be_op_assemble_pm(const float* params, const float* colors, size_t B, size_t L, float* pm, cudaStream_t st) {
+    k_assemble_pm<<<blocks_for(B * L * 38), TPB, 0, st>>>(params, colors, B, L, pm); ++g_be_launches;
+}
+void be_op_eval_depth(const float* pred, const float* gt, size_t N, int H, int W, int crop, double* out6, cudaStream_t st) {
+    dim3 grid(32, (unsigned)N);
+    k_eval_depth<<<grid, TPB, 0, st>>>(pred, gt, H, W, crop, 0.75f, 1.18f, 1.25f, out6); ++g_be_launches;
+}

@@ -170,6 +170,16 @@ int be_fold_depth(be_ctx* ctx, const float* dev_depth_map, const int32_t* dev_de
                   void* stream);
 int be_unfold(be_ctx* ctx, const float* dev_img, int64_t n, int32_t mode, float* dev_patches, void* stream);
 
+/* Glue of the inference driver around passes A and B (blurry_edges_test.py:119-148):
+ *   be_patch_gather   n images [n,3,H,W] -> vec [n*L,3,R,R], the LocalStage input (:119-121, Unfold + permute in one pass)
+ *   be_assemble_pm    n pairs: raw LocalStage params [2n,L,10] + colours [2n,3,3,Hp,Wp] -> GlobalStage input pm [n,L,38] (:123-132)
+ *   be_eval_depth     n images: thresholded depth + ground truth [n,H,W] -> per-image sums [n,6] (fp64): #valid, #acc<1.25,
+ *                     #acc<1.25^2, #acc<1.25^3, sum err^2, sum err/gt  (utils/metrics.py:3-21 with msk = depth>0, z in [0.75,1.18]) */
+int be_patch_gather(be_ctx* ctx, const float* dev_img, int64_t n, float* dev_vec, void* stream);
+int be_assemble_pm(be_ctx* ctx, const float* dev_params, const float* dev_colors, int64_t n, float* dev_pm, void* stream);
+int be_eval_depth(be_ctx* ctx, const float* dev_depth, const float* dev_gt, int64_t n, int32_t H, int32_t W, int32_t crop,
+                  double* dev_sums6, void* stream);
+
 /* Measurement hook: with timing enabled, be_render_fold_fwd brackets each of its four device operations with CUDA
  * events on the caller's stream; be_ctx_last_timing waits for the last call and returns their durations in ms:
  * ms4 = {accumulator memset, be_setup_kernel, be_run_kernel, be_normalise_kernel}. */
