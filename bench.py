@@ -10,7 +10,7 @@ processes its own batch of pairs (weak scaling, no data-path collective); time =
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
 C-ABI entry point with H2D/D2H copies inside the timed region, `roofline` the HBM roofline of the dominant kernel
-(be_run_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
+(be_run2_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
 `--impl reference` times the CPU port of the reference's eager PyTorch path (the reference itself is Python and is
 not present on the GPU box; oracle/be_oracle.py is pinned to it by tests/golden)."""
 from __future__ import annotations
@@ -42,6 +42,9 @@ ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
 # `ncu --set full` capture profiles/r1b_run2_kernel_full.txt (155.3 MB + 37.9 MB); None for other batch sizes
 TRAFFIC_NCU_64 = 155.325440e6 + 37.926400e6
 TRAFFIC_NCU = None
+# warp-instructions per patch of be_run2_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1c_run2_kernel_full.txt)
+WARP_INST_PER_PATCH = 6406.0
+SM_COUNT, SMSP_PER_SM = 148, 4
 
 
 def peaks():
@@ -310,6 +313,11 @@ def run_ours(args, rank, world, local_rank):
                         'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
                         'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
                                 'see profiles/ for pipe utilisation'},
+           'sm_issue': {'note': 'binding resource of the fused kernel: warp-instruction issue slots (1 per SMSP per clock)',
+                        'warp_inst_per_patch_ncu': WARP_INST_PER_PATCH,
+                        'achieved_ginst_per_s': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / 1e9,
+                        'peak_ginst_per_s': SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) / 1e3,
+                        'frac': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / (SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) * 1e6)},
            'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run_kernel': shares[2], 'be_normalise_kernel': shares[3]},
            'clocks': clk.summary(), 'wall_s_timed_region': t_wall}
     res.update(extra)
@@ -340,7 +348,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pairs', type=int, default=64, help='image pairs per GPU per step (BASELINE configs[1]: 64)')
-    ap.add_argument('--ref-pairs', type=int, default=4, help='pairs per step of the CPU reference sample')
+    ap.add_argument('--ref-pairs', type=int, default=8, help='pairs per step of the CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (train step, densify w, big image)')
     args = ap.parse_args()
