@@ -129,10 +129,12 @@ int validate_cfg(const be_config* cfg) {
     return 0;
 }
 
-// BE_RUN_V=1 selects the first-generation renderer (A/B measurements only)
+// BE_RUN_V=1|2 select the earlier generations of the renderer (A/B measurements only)
 void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) {
-    static const int v = [] { const char* e = getenv("BE_RUN_V"); return e ? atoi(e) : 2; }();
-    if (v == 1) be_launch_run(mode, a, st); else be_launch_run2(mode, a, st);
+    static const int v = [] { const char* e = getenv("BE_RUN_V"); return e ? atoi(e) : 3; }();
+    if (v == 1) be_launch_run(mode, a, st);
+    else if (v == 2) be_launch_run2(mode, a, st);
+    else be_launch_run3(mode, a, st);
 }
 
 // Split every patch row into `runs` runs of G consecutive patches (one CTA each).  Long runs amortise the sliding-window
@@ -464,7 +466,7 @@ int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, co
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors; a.blocks = c->blk_dev;
     a.g = c->g; a.cam = c->cam; a.NB = nitem; a.accH = c->g.H; a.accW = c->g.W;
     pick_runs(c->g, nitem, &a.G, &a.runs_per_row);
-    be_launch_run2(BE_RUN_COLORS, a, st);
+    launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -489,7 +491,7 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc; a.blocks = c->blk_dev;
     a.g = g; a.cam = c->cam; a.NB = nblk; a.densify_w = densify_w; a.accH = acc_H; a.accW = acc_W;
     pick_runs(g, nblk, &a.G, &a.runs_per_row);
-    be_launch_run2(BE_RUN_INFER, a, st);
+    launch_run(BE_RUN_INFER, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }
