@@ -29,8 +29,23 @@ template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("
 template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
 __device__ __forceinline__ void sync_full(int par) { if (par) bar_sync_id<2>(); else bar_sync_id<1>(); }
 __device__ __forceinline__ void arrive_full(int par) { if (par) bar_arrive_id<2>(); else bar_arrive_id<1>(); }
-__device__ __forceinline__ void sync_done(int par) { if (par) bar_sync_id<4>(); else bar_sync_id<3>(); }
-__device__ __forceinline__ void arrive_done(int par) { if (par) bar_arrive_id<4>(); else bar_arrive_id<3>(); }
+
+// DONE[parity] (colours published) is an mbarrier with one arrival (solver lane 0): a render warp waits for the solver only.
+// (A named barrier here made every render warp wait for all the others once per patch: 19 % of all warp time, ncu r1d.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{.reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
 
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
@@ -76,7 +91,8 @@ struct Smem {
     static constexpr size_t off_part = off_rec + sizeof(float) * 4 * BE_REC;        // float part[2][BE_WARPS][16]
     static constexpr size_t off_col = off_part + sizeof(float) * 2 * BE_WARPS * 16; // float col[2][16]: C0|-, D1|-, D2|-, ir1, ir2, z0, z1
     static constexpr size_t off_axis = off_col + sizeof(float) * 2 * 16;            // float axis[24]
-    static constexpr size_t bytes = off_axis + sizeof(float) * 24;
+    static constexpr size_t off_bar = off_axis + sizeof(float) * 24;                // mbarrier done[2]
+    static constexpr size_t bytes = off_bar + sizeof(unsigned long long) * 2;
 };
 
 template <int MODE>
@@ -94,6 +110,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
     float* s_part = reinterpret_cast<float*>(smem_raw + SM::off_part);
     float* s_col = reinterpret_cast<float*>(smem_raw + SM::off_col);
     float* s_axis = reinterpret_cast<float*>(smem_raw + SM::off_axis);
+    unsigned long long* s_done = reinterpret_cast<unsigned long long*>(smem_raw + SM::off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BeGeom g = a.g;
@@ -116,6 +133,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
 
     if (tid < R) s_axis[tid] = be_axis(tid, R);
+    if (tid == NTHR - 1) { mbar_init(s_done, 1); mbar_init(s_done + 1, 1); }
     if (tid < 16 && (tid >> 3) < n)   // records of patches 0 and 1
         reinterpret_cast<float4*>(s_rec)[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
     __syncthreads();
@@ -164,7 +182,8 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                 }
             }
             if (lane < 8 && k + 2 < n) reinterpret_cast<float4*>(s_rec + ((k + 2) & 3) * BE_REC)[lane] = nxt;
-            arrive_done(par);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_done + par);
         }
         return;
     }
@@ -191,16 +210,23 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
 
     auto load_pixel = [&](int s, int kpatch) {     // (re)load the pixel cache of slot s for the window of patch kpatch
         const int x = (px0 + kpatch) * g.stride + j[s], y = y0 + si[s];
-        float* base = reinterpret_cast<float*>(s_pix + tid) + s;
+        float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int m = 0; m < NIMG; ++m)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int q = 3 * m + c;
-                base[(q >> 1) * (NCOMP * 4) + (q & 1) * 2] = ld_img(a.img, ib, m, c, oy + y, ox + x);
-            }
-        if (TRAIN) base[3 * (NCOMP * 4)] = __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x);
-        asm volatile("" ::: "memory");     // the float stores above alias the float4 columns read by lds2
+            for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, ib, m, c, oy + y, ox + x);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {              // float4 read-modify-write keeps the column accesses conflict-free
+            float4 v = s_pix[q * NCOMP + tid];
+            if (s) { v.y = p[2 * q]; v.w = p[2 * q + 1]; } else { v.x = p[2 * q]; v.z = p[2 * q + 1]; }
+            s_pix[q * NCOMP + tid] = v;
+        }
+        if (TRAIN) {
+            const float zg = __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x);
+            float4 v = s_pix[3 * NCOMP + tid];
+            if (s) v.y = zg; else v.x = zg;
+            s_pix[3 * NCOMP + tid] = v;
+        }
     };
 #pragma unroll
     for (int q = 0; q < SM::NPIX4; ++q) s_pix[q * NCOMP + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -292,7 +318,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
         }
 
         // ---------------- phase 2 of patch k-1 ----------------
-        if (k >= 1) sync_done((k - 1) & 1);      // colours of patch k-1 are published; s_part[par] may be overwritten
+        if (k >= 1) mbar_wait(s_done + ((k - 1) & 1), ((k - 1) >> 1) & 1);   // colours of patch k-1 are published; s_part[par] is free
         if (FOLD && k >= 1) {
             const int kp = k - 1, par = kp & 1;
             const float4* col = reinterpret_cast<const float4*>(s_col + par * 16);
@@ -366,23 +392,18 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                 j2[s] = (jn < 0) ? jn + R : jn;
             }
             if (fl[0] || fl[1]) {
-                asm volatile("" ::: "memory");     // the scalar accesses below alias the float4 columns written by sts2
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     if (!fl[s]) continue;
                     float* dst = a.acc + (((size_t)ib * a.accH + oy + y0 + si[s]) * a.accW + ox + (px0 + kp) * g.stride + jc[s]) * ACCW;
-                    float* pa = reinterpret_cast<float*>(acc) + s;
 #pragma unroll
                     for (int q = 0; q < ACCW / 4; ++q) {
-                        float4 v;
-                        v.x = pa[(2 * q) * (NCOMP * 4)]; v.y = pa[(2 * q) * (NCOMP * 4) + 2];
-                        v.z = pa[(2 * q + 1) * (NCOMP * 4)]; v.w = pa[(2 * q + 1) * (NCOMP * 4) + 2];
-                        atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
-                        pa[(2 * q) * (NCOMP * 4)] = 0.0f; pa[(2 * q) * (NCOMP * 4) + 2] = 0.0f;
-                        pa[(2 * q + 1) * (NCOMP * 4)] = 0.0f; pa[(2 * q + 1) * (NCOMP * 4) + 2] = 0.0f;
+                        float4 v0 = acc[(2 * q) * NCOMP], v1 = acc[(2 * q + 1) * NCOMP];
+                        atomicAdd(reinterpret_cast<float4*>(dst) + q, s ? make_float4(v0.y, v0.w, v1.y, v1.w) : make_float4(v0.x, v0.z, v1.x, v1.z));
+                        if (s) { v0.y = v0.w = v1.y = v1.w = 0.0f; } else { v0.x = v0.z = v1.x = v1.z = 0.0f; }
+                        acc[(2 * q) * NCOMP] = v0; acc[(2 * q + 1) * NCOMP] = v1;
                     }
                 }
-                asm volatile("" ::: "memory");
             }
         }
     }
