@@ -64,9 +64,10 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     return d;
 }
 
-__device__ __forceinline__ float ld_img(const BeImg& im, int b, int m, int c, int y, int x) {
-    return __ldg(im.p + b * im.sb + m * im.sm + c * im.sc + y * im.sy + x * im.sx);
+__device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // a float4 of shared memory seen as two packed pairs
 struct f2x2 { f2 a, b; };
@@ -208,25 +209,20 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
     const f2 Y = mk2(s_axis[si[0]], s_axis[si[1]]);
     const float vm1 = valid[1] ? 1.0f : 0.0f;     // weight of the second slot in the normal-equation sums
 
-    auto load_pixel = [&](int s, int kpatch) {     // (re)load the pixel cache of slot s for the window of patch kpatch
+    // (Re)load the pixel cache of slot s for the window of patch kpatch with 4-byte cp.async copies straight into the slot's
+    // half of the (slot0, slot1) pairs: the warp does not wait for the pixels (they are first read in phase 1 of the next patch,
+    // after cp_async_wait), so a warp whose column wraps no longer arrives late at the solver hand-off.
+    auto load_pixel = [&](int s, int kpatch) {
         const int x = (px0 + kpatch) * g.stride + j[s], y = y0 + si[s];
-        float p[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const unsigned base = smem_u32(s_pix + tid) + 4u * s;
 #pragma unroll
         for (int m = 0; m < NIMG; ++m)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) p[3 * m + c] = ld_img(a.img, ib, m, c, oy + y, ox + x);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {              // float4 read-modify-write keeps the column accesses conflict-free
-            float4 v = s_pix[q * NCOMP + tid];
-            if (s) { v.y = p[2 * q]; v.w = p[2 * q + 1]; } else { v.x = p[2 * q]; v.z = p[2 * q + 1]; }
-            s_pix[q * NCOMP + tid] = v;
-        }
-        if (TRAIN) {
-            const float zg = __ldg(a.zgt + ((size_t)b * g.H + y) * g.W + x);
-            float4 v = s_pix[3 * NCOMP + tid];
-            if (s) v.y = zg; else v.x = zg;
-            s_pix[3 * NCOMP + tid] = v;
-        }
+            for (int c = 0; c < 3; ++c) {
+                const int q = 3 * m + c;
+                cp_async4(base + (q >> 1) * (NCOMP * 16) + (q & 1) * 8, a.img.p + ib * a.img.sb + m * a.img.sm + c * a.img.sc + (oy + y) * a.img.sy + (ox + x) * a.img.sx);
+            }
+        if (TRAIN) cp_async4(base + 3 * (NCOMP * 16), a.zgt + ((size_t)b * g.H + y) * g.W + x);
     };
 #pragma unroll
     for (int q = 0; q < SM::NPIX4; ++q) s_pix[q * NCOMP + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -255,6 +251,7 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
             f2 d1, d2;
             be_pixel_dists2(P, X, Y, g.w, &d1, &d2);
             f2 pix[6];
+            cp_async_wait();
             {
                 const f2x2 v0 = lds2(s_pix + tid), v1 = lds2(s_pix + NCOMP + tid), v2 = lds2(s_pix + 2 * NCOMP + tid);
                 pix[0] = v0.a; pix[1] = v0.b; pix[2] = v1.a; pix[3] = v1.b; pix[4] = v2.a; pix[5] = v2.b;
