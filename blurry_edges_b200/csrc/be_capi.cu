@@ -61,6 +61,7 @@ struct be_ctx {
     cudaEvent_t blk_ev;
     // training workspace (lazily allocated by the loss entry points)
     float* gtable;      // [max_batch*L][BE_GREC]
+    float* crec;        // [max_batch*L][BE_CREC]
     float* T;           // [max_batch][H][W][BE_TW]
     float* partials;    // [max_batch*Hp*runs][8]
     size_t train_bytes;
@@ -207,7 +208,7 @@ int be_ctx_destroy(be_ctx* c) {
     if (!c) return 0;
     cudaFree(c->table); cudaFree(c->acc);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
-    cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials);
+    cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec);
     cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
     if (c->blk_ev) cudaEventDestroy(c->blk_ev);
     for (int i = 0; i < 3; ++i) if (c->st_streams[i]) cudaStreamDestroy(c->st_streams[i]);
@@ -324,10 +325,12 @@ static int ensure_train_ws(be_ctx* c) {
     const int runs = (g.Wp + 7) / 8;   // worst case of pick_runs
     const size_t b1 = mb * L * BE_GREC * sizeof(float), b2 = mb * g.H * g.W * BE_TW * sizeof(float);
     const size_t b3 = mb * g.Hp * runs * 8 * sizeof(float);
+    const size_t b4 = mb * L * BE_CREC * sizeof(float);
     BE_CUDA(cudaMalloc(&c->gtable, b1));
     BE_CUDA(cudaMalloc(&c->T, b2));
     BE_CUDA(cudaMalloc(&c->partials, b3));
-    c->train_bytes = b1 + b2 + b3;
+    BE_CUDA(cudaMalloc(&c->crec, b4));
+    c->train_bytes = b1 + b2 + b3 + b4;
     return 0;
 }
 
@@ -351,9 +354,10 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.table = c->table; a.acc = c->acc;
     a.img.p = dev_img_ny; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
     a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
+    a.crec = c->crec;
     a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
     pick_runs(g, B, &a.G, &a.runs_per_row);
-    launch_run(BE_RUN_TRAINFWD, a, st);
+    be_launch_run3(BE_RUN_TRAINFWD, a, st);   // the loss kernel needs the colour records only this generation writes
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
     BE_CUDA(cudaGetLastError());
@@ -373,7 +377,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)global_patches;
     BeLossArgs a;
     memset(&a, 0, sizeof(a));
-    a.table = c->table; a.gtable = c->gtable; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
+    a.table = c->table; a.gtable = c->gtable; a.crec = c->crec; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
     a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
     a.g = g; a.NB = B;
     pick_runs(g, B, &a.G, &a.runs_per_row);
@@ -385,7 +389,8 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     a.kc = (float)(gammas7[0] / norm[0]); a.kcc = (float)(gammas7[1] / norm[1]); a.kbc = (float)(gammas7[2] / norm[2]);
     a.ks = (float)(gammas7[3] / norm[3]); a.ksc = (float)(gammas7[4] / norm[4]); a.kbl = (float)(gammas7[5] / norm[5]);
     a.gamma_d = (float)gammas7[6];
-    be_launch_loss(false, a, st);
+    static const int v = [] { const char* e = getenv("BE_LOSS_V"); return e ? atoi(e) : 2; }();   // 1: first-generation kernel (A/B runs)
+    if (v == 1) be_launch_loss(false, a, st); else be_launch_loss2(a, st);
     be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
     BE_CUDA(cudaGetLastError());
     return 0;

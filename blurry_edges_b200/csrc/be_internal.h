@@ -11,6 +11,7 @@ constexpr int BE_WARPS = BE_THREADS / 32;
 constexpr int BE_REC = 32;            // floats per patch-table record (128 B)
 constexpr int BE_ACC = 16;            // floats per pixel of the fold accumulator (15 used)
 constexpr int BE_GREC = 12;           // floats per patch of the backward chain-rule record
+constexpr int BE_CREC = 16;           // floats per patch of the colour record of the TRAINFWD pass: C[9], M^-1[6] (packed 00,01,02,11,12,22)
 constexpr int BE_TW = 36;             // floats per pixel of the packed training-target record (be_train.cu)
 
 enum BeRunMode { BE_RUN_COLORS = 0, BE_RUN_INFER = 1, BE_RUN_TRAINFWD = 2 };
@@ -44,6 +45,7 @@ struct BeRunArgs {
     int NB;                           // pairs (INFER) or single images (COLORS)
     int G, runs_per_row;              // patches per CTA run, runs per patch row
     int densify_w;
+    float* crec;                      // [NB*L][BE_CREC] colours + inverse normal matrix per patch (TRAINFWD, optional)
     const BeBlock* blocks;            // nullptr: item b is pair/image b at origin (0,0), all patches
     int accH, accW;                   // accumulator plane size (= H, W unless blocked)
 };
@@ -51,6 +53,7 @@ struct BeRunArgs {
 struct BeLossArgs {
     const float* table;               // [N][BE_REC]
     const float* gtable;              // [N][BE_GREC]
+    const float* crec;                // [N][BE_CREC] (global loss: written by the TRAINFWD pass)
     const float* T;                   // [NB][H][W][BE_TW] packed targets (global loss)
     const float *l_ny, *l_gt, *l_bd, *l_deri;   // local loss: [NB,R,R,3], [NB,R,R,3], [NB,R,R], [NB,R-2,R-2,3]
     float* grad;                      // [N][12|10] or nullptr
@@ -74,7 +77,8 @@ void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& 
 void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st);
 void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
                           const float* bndry_depth, float* T, cudaStream_t st);
-void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st);
+void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st);   // first generation; the local-stage loss
+void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
 void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
                            float* loss, cudaStream_t st);
 void be_launch_run(int mode, const BeRunArgs& a, cudaStream_t st);    // first generation (kept for A/B checks)

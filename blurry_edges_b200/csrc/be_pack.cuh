@@ -93,3 +93,65 @@ BE_HD void be_mask_weights(float d1, float d2, bool densify_w, float* m1, float*
     *m1 = (mk == 1) ? 1.0f : 0.0f;
     *m2 = (mk == 2) ? 1.0f : 0.0f;
 }
+
+// ------------------------------------------------------------------------------------------
+// backward pieces, two pixels at a time (be_math.cuh: be_h_grad, be_wedges_backward, be_boundary_backward, be_wedge_backward)
+BE_HD f2 neg2(f2 a) { return mk2(-lo(a), -hi(a)); }
+BE_HD f2 sel2(bool c0, bool c1, f2 a, f2 b) { return mk2(c0 ? lo(a) : lo(b), c1 ? hi(a) : hi(b)); }
+BE_HD float be_sign(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
+
+BE_HD void be_h_grad2(f2 dist, float inv_eta, f2* dh_dd, f2* dh_deta) {
+    const f2 t = mul2(dist, bc2(inv_eta));
+    const f2 x = mul2(mul2(t, t), bc2(-1.44269504f));
+    const f2 e = mul2(bc2(BE_INV_SQRT_PI), mk2(be_exp2(lo(x)), be_exp2(hi(x))));
+    *dh_dd = mul2(e, bc2(inv_eta));
+    *dh_deta = mul2(mul2(neg2(e), t), bc2(BE_SQRT2_F * inv_eta));
+}
+
+BE_HD void be_boundary_backward1(float d1, float d2, float lb, float glb, float* gd1, float* gd2) {
+    float a = 0.0f, b = 0.0f;
+    be_boundary_backward(d1, d2, lb, glb, &a, &b);
+    *gd1 = a; *gd2 = b;
+}
+
+// one edge of be_wedge_backward for one pixel: contributions (gd, ga) of dL/d|D| routed through D = a<0 ? sign(d) r : d
+BE_HD void be_edge_backward1(float d, float a, float absD, float sgw, float w2, float* gd, float* ga) {
+    if (a < 0.0f) {
+        const float ir = (absD > 0.0f) ? 1.0f / absD : 0.0f;
+        *gd = sgw * d * ir; *ga = sgw * w2 * a * ir;
+    } else {
+        *gd = sgw * be_sign(d); *ga = 0.0f;
+    }
+}
+
+// be_wedge_backward for two pixels; acc[0..3] are packed partial sums (vertex x, vertex y, angle A, angle B)
+BE_HD void be_wedge_backward2(const BePatch& P, int k, f2 X, f2 Y, float w, f2 g, f2* acc) {
+    const f2 dx = sub2(X, bc2(P.vx[k])), dy = sub2(Y, bc2(P.vy[k]));
+    const float f = P.flip[k];
+    const float snA = P.sn[2 * k], csA = P.cs[2 * k], snB = P.sn[2 * k + 1], csB = P.cs[2 * k + 1];
+    const f2 dA = fma2(bc2(csA), dy, mul2(bc2(-snA), dx)), aA = fma2(bc2(csA), dx, mul2(bc2(snA), dy));
+    const f2 dB = fma2(bc2(csB), dy, mul2(bc2(-snB), dx)), aB = fma2(bc2(csB), dx, mul2(bc2(snB), dy));
+    const f2 awA = mul2(aA, bc2(w)), awB = mul2(aB, bc2(w));
+    const f2 cA2 = fma2(dA, dA, mul2(awA, awA)), cB2 = fma2(dB, dB, mul2(awB, awB));
+    float gdA[2], gaA[2], gdB[2], gaB[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const float dAs = s ? hi(dA) : lo(dA), aAs = s ? hi(aA) : lo(aA), dBs = s ? hi(dB) : lo(dB), aBs = s ? hi(aB) : lo(aB);
+        const float capA = be_sqrt(s ? hi(cA2) : lo(cA2)), capB = be_sqrt(s ? hi(cB2) : lo(cB2));
+        const float DA = (aAs < 0.0f) ? ((dAs < 0.0f) ? -capA : capA) : dAs;
+        const float DB = (aBs < 0.0f) ? ((dBs < 0.0f) ? -capB : capB) : dBs;
+        const bool in = (k == 0) ? ((f * DA > 0.0f) && (f * DB < 0.0f)) : ((f * DA >= 0.0f) && (f * DB <= 0.0f));
+        const float sg = (s ? hi(g) : lo(g)) * (in ? f : -f);
+        const float absA = fabsf(DA), absB = fabsf(DB);
+        const float wA = (absA < absB) ? 1.0f : ((absA == absB) ? 0.5f : 0.0f);
+        be_edge_backward1(dAs, aAs, absA, sg * wA, w * w, &gdA[s], &gaA[s]);
+        be_edge_backward1(dBs, aBs, absB, sg * (1.0f - wA), w * w, &gdB[s], &gaB[s]);
+    }
+    const f2 GdA = mk2(gdA[0], gdA[1]), GaA = mk2(gaA[0], gaA[1]), GdB = mk2(gdB[0], gdB[1]), GaB = mk2(gaB[0], gaB[1]);
+    // acc[0] += (gdA snA - gaA csA) + (gdB snB - gaB csB)
+    acc[0] = add2(acc[0], add2(fma2(GdA, bc2(snA), mul2(GaA, bc2(-csA))), fma2(GdB, bc2(snB), mul2(GaB, bc2(-csB)))));
+    // acc[1] += (-gdA csA - gaA snA) + (-gdB csB - gaB snB)
+    acc[1] = add2(acc[1], add2(fma2(GdA, bc2(-csA), mul2(GaA, bc2(-snA))), fma2(GdB, bc2(-csB), mul2(GaB, bc2(-snB)))));
+    acc[2] = add2(acc[2], fma2(GaA, dA, mul2(neg2(GdA), aA)));     // -gdA aA + gaA dA
+    acc[3] = add2(acc[3], fma2(GaB, dB, mul2(neg2(GdB), aB)));
+}

@@ -165,6 +165,13 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                     col[0] = make_float4(C[0], C[1], C[2], 0.0f);
                     col[1] = make_float4(C[3] - C[0], C[4] - C[1], C[5] - C[2], 0.0f);
                     col[2] = make_float4(C[6] - C[0], C[7] - C[1], C[8] - C[2], 0.0f);
+                    if (TRAIN && a.crec != nullptr) {     // colours + M^-1 for the loss kernel (be_loss2.cu)
+                        float4* cr = reinterpret_cast<float4*>(a.crec + (patch0 + k) * BE_CREC);
+                        cr[0] = make_float4(C[0], C[1], C[2], C[3]);
+                        cr[1] = make_float4(C[4], C[5], C[6], C[7]);
+                        cr[2] = make_float4(C[8], (float)Minv[0], (float)Minv[1], (float)Minv[2]);
+                        cr[3] = make_float4((float)Minv[3], (float)Minv[4], (float)Minv[5], 0.0f);
+                    }
                     if (INFER) {
                         const float* rec = s_rec + (k & 3) * BE_REC;
                         const float z0 = rec[14], z1 = rec[15];
