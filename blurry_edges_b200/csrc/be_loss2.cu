@@ -19,6 +19,7 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NT = BE_THREADS;               // 224 threads, 7 warps, two pixel slots per thread
 constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
+constexpr int GMAX = (BE_MAX_R + 2) * (BE_MAX_R + 2);
 
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
@@ -37,7 +38,8 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     return d;
 }
 
-__global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
+template <int RCT>   // RCT = 21: patch size known at compile time (neighbour offsets become immediates), 0: generic
+__global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
     __shared__ __align__(16) float s_rec[2][BE_REC];
     __shared__ __align__(16) float s_grec[2][BE_GREC];
     __shared__ __align__(16) float s_crec[2][BE_CREC];
@@ -46,13 +48,13 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
     __shared__ float s_part3[BE_WARPS][16];
     __shared__ float4 s_Pa[RRMAX];
     __shared__ float2 s_Pb[RRMAX];
-    __shared__ float4 s_gxa[RRMAX], s_gya[RRMAX];
-    __shared__ float2 s_gxb[RRMAX], s_gyb[RRMAX];
+    __shared__ float4 s_gxa[GMAX], s_gya[GMAX];   // Sobel gradients with a one-pixel zero halo: the adjoint needs no bounds checks
+    __shared__ float2 s_gxb[GMAX], s_gyb[GMAX];
     __shared__ float4 s_stash[2][NT];            // thread-private: (d1, d2) and (global boundary, bndry_dist) pairs, stage A -> D
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BeGeom g = a.g;
-    const int R = g.R, RR = R * R;
+    const int R = RCT ? RCT : g.R, RR = R * R;
 
     int blk = blockIdx.x;
     const int run = blk % a.runs_per_row; blk /= a.runs_per_row;
@@ -87,10 +89,12 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
         q[s] = valid[s] ? qq : 0;
         pi[s] = q[s] / R; pj[s] = q[s] % R;
         interior[s] = valid[s] && pi[s] >= 1 && pi[s] <= R - 2 && pj[s] >= 1 && pj[s] <= R - 2;
-        if (qq < RRMAX) {   // border entries of the Sobel-gradient planes stay zero for the whole kernel
-            s_gxa[qq] = s_gya[qq] = make_float4(0.f, 0.f, 0.f, 0.f);
-            s_gxb[qq] = s_gyb[qq] = make_float2(0.f, 0.f);
-        }
+    }
+    const int RG = R + 2;
+    const int qg[2] = {(pi[0] + 1) * RG + pj[0] + 1, (pi[1] + 1) * RG + pj[1] + 1};
+    for (int i = tid; i < GMAX; i += NT) {   // halo and border entries of the Sobel-gradient planes stay zero for the whole kernel
+        s_gxa[i] = s_gya[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s_gxb[i] = s_gyb[i] = make_float2(0.f, 0.f);
     }
     __syncthreads();
     const f2 Y = mk2(s_axis[pi[0]], s_axis[pi[1]]), X = mk2(s_axis[pj[0]], s_axis[pj[1]]);
@@ -159,6 +163,15 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
             float C[9];
             load_patch(P);
             load_colors(C);
+            float2 t1[2];
+            float4 t2[2], t3[2], t4[2];                  // targets: issued before the arithmetic that hides their latency
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                t1[s] = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS + 2));
+                t2[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 2 * TPS));
+                t3[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 3 * TPS));
+                t4[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 4 * TPS));
+            }
             f2 d1, d2;
             be_pixel_dists2(P, X, Y, g.w, &d1, &d2);
             f2 Pv[6];
@@ -181,13 +194,9 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
                     s_Pa[q[s]] = make_float4(pv[0], pv[1], pv[2], pv[3]);
                     s_Pb[q[s]] = make_float2(pv[4], pv[5]);
                 }
-                const float2 t1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS + 2));
-                const float4 t2 = __ldg(reinterpret_cast<const float4*>(tp[s] + 2 * TPS));
-                const float4 t3 = __ldg(reinterpret_cast<const float4*>(tp[s] + 3 * TPS));
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp[s] + 4 * TPS));
-                const float gt[6] = {t1.x, t1.y, t2.x, t2.y, t2.z, t2.w};
-                const float gi[6] = {t3.x, t3.y, t3.z, t3.w, t4.x, t4.y};
-                gb_[s] = t4.z; bd_[s] = t4.w;
+                const float gt[6] = {t1[s].x, t1[s].y, t2[s].x, t2[s].y, t2[s].z, t2[s].w};
+                const float gi[6] = {t3[s].x, t3[s].y, t3[s].z, t3[s].w, t4[s].x, t4[s].y};
+                gb_[s] = t4[s].z; bd_[s] = t4[s].w;
                 float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
@@ -213,6 +222,9 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (interior[s]) {
+                const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
+                const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
+                const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
                 float sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sy[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int oi = -1; oi <= 1; ++oi)
@@ -231,16 +243,13 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
                             if (wy != 0.0f) sy[c] = fmaf(wy, pv[c], sy[c]);
                         }
                     }
-                const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
-                const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
-                const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
                 const float dgt[6] = {t6.x, t6.y, t6.z, t6.w, t7.x, t7.y};
                 const float dgi[6] = {t7.z, t7.w, t8.x, t8.y, t8.z, t8.w};
                 float gx[6], gy[6], l3 = 0.0f, l4 = 0.0f;
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
                     const float v = fmaf(sx[c], sx[c], fmaf(sy[c], sy[c], 1e-8f));
-                    const float ir = rsqrtf(v);
+                    const float ir = be_rsqrt(v);        // v >= 1e-8: no denormal handling needed
                     const float mag = v * ir;
                     const float e1 = mag - dgt[c], e2 = mag - dgi[c];
                     l3 = fmaf(e1, e1, l3);
@@ -250,10 +259,10 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
                     gy[c] = gm * sy[c];
                 }
                 lossacc[3] += l3; lossacc[4] += l4;      // interior slots are valid slots
-                s_gxa[q[s]] = make_float4(gx[0], gx[1], gx[2], gx[3]);
-                s_gxb[q[s]] = make_float2(gx[4], gx[5]);
-                s_gya[q[s]] = make_float4(gy[0], gy[1], gy[2], gy[3]);
-                s_gyb[q[s]] = make_float2(gy[4], gy[5]);
+                s_gxa[qg[s]] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+                s_gxb[qg[s]] = make_float2(gx[4], gx[5]);
+                s_gya[qg[s]] = make_float4(gy[0], gy[1], gy[2], gy[3]);
+                s_gyb[qg[s]] = make_float2(gy[4], gy[5]);
             }
         }
         __syncthreads();   // (X2) Sobel gradients visible
@@ -272,11 +281,9 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
                         for (int dj = -1; dj <= 1; ++dj) {
                             if (di == 0 && dj == 0) continue;
-                            const int io = pi[s] + di, jo = pj[s] + dj;
-                            if (io < 0 || io >= R || jo < 0 || jo >= R) continue;
                             const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
                             const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
-                            const int qn = q[s] + di * R + dj;
+                            const int qn = qg[s] + di * RG + dj;
                             if (wx != 0.0f) {
                                 const float4 ga = s_gxa[qn];
                                 const float2 gb = s_gxb[qn];
@@ -322,6 +329,15 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
             float C[9];
             load_patch(P);
             load_colors(C);
+            float ny[2][6];
+            float zgv[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
+                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS));
+                ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
+                zgv[s] = __ldg(tp[s] + 5 * TPS);
+            }
             const float4 sd = s_stash[0][tid], sg = s_stash[1][tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);
             float V[9], Ssym[6];
@@ -356,15 +372,6 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
             f2 sums[14];
 #pragma unroll
             for (int i = 0; i < 14; ++i) sums[i] = bc2(0.0f);
-            float ny[2][6];
-            float zgv[2];
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
-                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS));
-                ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
-                zgv[s] = __ldg(tp[s] + 5 * TPS);
-            }
             f2 gd1 = bc2(0.0f), gd2 = bc2(0.0f);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -449,6 +456,7 @@ __global__ void __maxnreg__(96) be_loss2_kernel(const BeLossArgs a) {
 
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    be_loss2_kernel<<<grid, NT, 0, st>>>(a);
+    if (a.g.R == 21) be_loss2_kernel<21><<<grid, NT, 0, st>>>(a);
+    else be_loss2_kernel<0><<<grid, NT, 0, st>>>(a);
     ++g_be_launches;
 }

@@ -97,6 +97,26 @@ BE_HD float be_sqrt(float x) {
 #endif
 }
 
+BE_HD float be_rsqrt(float x) {   // MUFU.RSQ (<= 2 ulp)
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
+BE_HD float be_rcp(float x) {     // MUFU.RCP (<= 1 ulp)
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
 BE_HD float be_eta(float coef) { return be_exp10(erff(coef) * 2.0f - 2.0f); }   // :88-89
 
 // sin/cos of (a + b) where a, b are fp32 angles: evaluate at s = fl(a+b) and correct with the exact

@@ -117,7 +117,7 @@ BE_HD void be_boundary_backward1(float d1, float d2, float lb, float glb, float*
 // one edge of be_wedge_backward for one pixel: contributions (gd, ga) of dL/d|D| routed through D = a<0 ? sign(d) r : d
 BE_HD void be_edge_backward1(float d, float a, float absD, float sgw, float w2, float* gd, float* ga) {
     if (a < 0.0f) {
-        const float ir = (absD > 0.0f) ? 1.0f / absD : 0.0f;
+        const float ir = (absD > 0.0f) ? be_rcp(absD) : 0.0f;
         *gd = sgw * d * ir; *ga = sgw * w2 * a * ir;
     } else {
         *gd = sgw * be_sign(d); *ga = 0.0f;
