@@ -19,7 +19,8 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NT = BE_THREADS;               // 224 threads, 7 warps, two pixel slots per thread
 constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
-constexpr int GMAX = (BE_MAX_R + 2) * (BE_MAX_R + 2);
+constexpr int HALO = BE_MAX_R + 1;
+constexpr int NE = NT + 2 * HALO;
 
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
@@ -46,10 +47,14 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
     __shared__ float s_axis[BE_MAX_R + 3];
     __shared__ float s_part[BE_WARPS][16];
     __shared__ float s_part3[BE_WARPS][16];
-    __shared__ float4 s_Pa[RRMAX];
-    __shared__ float2 s_Pb[RRMAX];
-    __shared__ float4 s_gxa[GMAX], s_gya[GMAX];   // Sobel gradients with a one-pixel zero halo: the adjoint needs no bounds checks
-    __shared__ float2 s_gxb[GMAX], s_gyb[GMAX];
+    // Stencil exchange planes in PAIR layout: entry e holds, per channel, (value at pixel e-HALO, value at pixel e-HALO+NT), so the
+    // neighbour of both slots of thread t at offset `off` is the one entry t+HALO+off (3 LDS.128 for 6 channels of two pixels).
+    // Pixels within HALO of the seam are written twice (as the low half of their own entry and as the high half of the entry NT
+    // below); entries outside the patch stay zero.  Row wrap-around needs no mask: a wrapped neighbour is a border pixel, whose
+    // Sobel gradients are zero, and only interior pixels (which never wrap) use the rendered-patch plane.
+    __shared__ float4 s_X[9 * NE];
+    float4* const s_P2 = s_X;                     // [3][NE] rendered patch: (c0,c1) (c2,c3) (c4,c5)
+    float4* const s_G2 = s_X + 3 * NE;            // [6][NE] Sobel gradients: gx (c0,c1) (c2,c3) (c4,c5), gy (c0,c1) (c2,c3) (c4,c5)
     __shared__ float4 s_stash[2][NT];            // thread-private: (d1, d2) and (global boundary, bndry_dist) pairs, stage A -> D
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -90,12 +95,27 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
         pi[s] = q[s] / R; pj[s] = q[s] % R;
         interior[s] = valid[s] && pi[s] >= 1 && pi[s] <= R - 2 && pj[s] >= 1 && pj[s] <= R - 2;
     }
-    const int RG = R + 2;
-    const int qg[2] = {(pi[0] + 1) * RG + pj[0] + 1, (pi[1] + 1) * RG + pj[1] + 1};
-    for (int i = tid; i < GMAX; i += NT) {   // halo and border entries of the Sobel-gradient planes stay zero for the whole kernel
-        s_gxa[i] = s_gya[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        s_gxb[i] = s_gyb[i] = make_float2(0.f, 0.f);
-    }
+    for (int i = tid; i < 9 * NE; i += NT) s_X[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // store one pair-layout entry (+ the duplicates near the seam) of `nch` channels given as (slot0, slot1) pairs
+    auto store_pairs = [&](float4* plane0, const f2* v, int nch) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (2 * k < nch) plane0[k * NE + tid + HALO] = make_float4(lo(v[2 * k]), hi(v[2 * k]), lo(v[2 * k + 1]), hi(v[2 * k + 1]));
+        if (tid >= NT - HALO) {                    // my low pixel is also the high half of entry tid - NT
+            float* d = reinterpret_cast<float*>(plane0 + (tid - NT + HALO)) + 1;
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                if (c < nch) d[(c >> 1) * (NE * 4) + (c & 1) * 2] = lo(v[c]);
+        }
+        if (tid < HALO) {                          // my high pixel is also the low half of entry tid + NT
+            float* d = reinterpret_cast<float*>(plane0 + (tid + NT + HALO));
+#pragma unroll
+            for (int c = 0; c < 12; ++c)
+                if (c < nch) d[(c >> 1) * (NE * 4) + (c & 1) * 2] = hi(v[c]);
+        }
+    };
+    const f2 mI = mk2(interior[0] ? 1.0f : 0.0f, interior[1] ? 1.0f : 0.0f);
+    const f2 kIs = mul2(bc2(2.0f * a.ks), mI), kIsc = mul2(bc2(2.0f * a.ksc), mI);    // Sobel-loss weights, zero off the interior
     __syncthreads();
     const f2 Y = mk2(s_axis[pi[0]], s_axis[pi[1]]), X = mk2(s_axis[pj[0]], s_axis[pj[1]]);
     const float vm0 = valid[0] ? 1.0f : 0.0f, vm1 = valid[1] ? 1.0f : 0.0f;
@@ -184,16 +204,13 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) Pv[3 * m + c] = fma2(u0, bc2(C[c]), fma2(u1, bc2(C[3 + c]), mul2(u2, bc2(C[6 + c]))));
             }
+            store_pairs(s_P2, Pv, 6);
             float gb_[2], bd_[2], Gs[2][6];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 float pv[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pv[c] = s ? hi(Pv[c]) : lo(Pv[c]);
-                if (valid[s]) {
-                    s_Pa[q[s]] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                    s_Pb[q[s]] = make_float2(pv[4], pv[5]);
-                }
                 const float gt[6] = {t1[s].x, t1[s].y, t2[s].x, t2[s].y, t2[s].z, t2[s].w};
                 const float gi[6] = {t3[s].x, t3[s].y, t3[s].z, t3[s].w, t4[s].x, t4[s].y};
                 gb_[s] = t4[s].z; bd_[s] = t4[s].w;
@@ -218,91 +235,79 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
         // chain rule of the previous patch, by one warp, while the others go on
         if (k >= 1 && warp == (k - 1) % BE_WARPS) chain(k - 1);
 
-        // ---------------- stage B: Sobel magnitude of the rendered patch, its loss and gradient ----------------
+        // ---------------- stage B: Sobel magnitude of the rendered patch, its loss and gradient (both slots packed) ----------------
+        {
+            float4 t6[2], t7[2], t8[2];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (interior[s]) {
-                const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
-                const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
-                const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
-                float sx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sy[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int oi = -1; oi <= 1; ++oi)
-#pragma unroll
-                    for (int oj = -1; oj <= 1; ++oj) {
-                        if (oi == 0 && oj == 0) continue;
-                        const float wx = (float)(((oi == 0) ? 2 : 1) * oj);       // sobel_x[oi+1][oj+1]
-                        const float wy = (float)(-oi * ((oj == 0) ? 2 : 1));      // sobel_y[oi+1][oj+1]
-                        const int qn = q[s] + oi * R + oj;
-                        const float4 pa = s_Pa[qn];
-                        const float2 pb = s_Pb[qn];
-                        const float pv[6] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y};
-#pragma unroll
-                        for (int c = 0; c < 6; ++c) {
-                            if (wx != 0.0f) sx[c] = fmaf(wx, pv[c], sx[c]);
-                            if (wy != 0.0f) sy[c] = fmaf(wy, pv[c], sy[c]);
-                        }
-                    }
-                const float dgt[6] = {t6.x, t6.y, t6.z, t6.w, t7.x, t7.y};
-                const float dgi[6] = {t7.z, t7.w, t8.x, t8.y, t8.z, t8.w};
-                float gx[6], gy[6], l3 = 0.0f, l4 = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    const float v = fmaf(sx[c], sx[c], fmaf(sy[c], sy[c], 1e-8f));
-                    const float ir = be_rsqrt(v);        // v >= 1e-8: no denormal handling needed
-                    const float mag = v * ir;
-                    const float e1 = mag - dgt[c], e2 = mag - dgi[c];
-                    l3 = fmaf(e1, e1, l3);
-                    l4 = fmaf(e2, e2, l4);
-                    const float gm = fmaf(2.0f * a.ksc, e2, 2.0f * a.ks * e1) * ir;
-                    gx[c] = gm * sx[c];
-                    gy[c] = gm * sy[c];
-                }
-                lossacc[3] += l3; lossacc[4] += l4;      // interior slots are valid slots
-                s_gxa[qg[s]] = make_float4(gx[0], gx[1], gx[2], gx[3]);
-                s_gxb[qg[s]] = make_float2(gx[4], gx[5]);
-                s_gya[qg[s]] = make_float4(gy[0], gy[1], gy[2], gy[3]);
-                s_gyb[qg[s]] = make_float2(gy[4], gy[5]);
+            for (int s = 0; s < 2; ++s) {
+                t6[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
+                t7[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
+                t8[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
             }
+            f2 sx[6], sy[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sx[c] = sy[c] = bc2(0.0f);
+#pragma unroll
+            for (int oi = -1; oi <= 1; ++oi)
+#pragma unroll
+                for (int oj = -1; oj <= 1; ++oj) {
+                    if (oi == 0 && oj == 0) continue;
+                    const float wx = (float)(((oi == 0) ? 2 : 1) * oj);       // sobel_x[oi+1][oj+1]
+                    const float wy = (float)(-oi * ((oj == 0) ? 2 : 1));      // sobel_y[oi+1][oj+1]
+                    const float4* pn = s_P2 + (tid + HALO + oi * R + oj);
+                    const float4 v0 = pn[0], v1 = pn[NE], v2 = pn[2 * NE];
+                    const f2 pv[6] = {mk2(v0.x, v0.y), mk2(v0.z, v0.w), mk2(v1.x, v1.y), mk2(v1.z, v1.w), mk2(v2.x, v2.y), mk2(v2.z, v2.w)};
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        if (wx != 0.0f) sx[c] = fma2(bc2(wx), pv[c], sx[c]);
+                        if (wy != 0.0f) sy[c] = fma2(bc2(wy), pv[c], sy[c]);
+                    }
+                }
+            const float dgt[2][6] = {{t6[0].x, t6[0].y, t6[0].z, t6[0].w, t7[0].x, t7[0].y}, {t6[1].x, t6[1].y, t6[1].z, t6[1].w, t7[1].x, t7[1].y}};
+            const float dgi[2][6] = {{t7[0].z, t7[0].w, t8[0].x, t8[0].y, t8[0].z, t8[0].w}, {t7[1].z, t7[1].w, t8[1].x, t8[1].y, t8[1].z, t8[1].w}};
+            f2 gxy[12], l3 = bc2(0.0f), l4 = bc2(0.0f);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const f2 v = fma2(sx[c], sx[c], fma2(sy[c], sy[c], bc2(1e-8f)));
+                const f2 ir = mk2(be_rsqrt(lo(v)), be_rsqrt(hi(v)));          // v >= 1e-8: no denormal handling needed
+                const f2 mag = mul2(v, ir);
+                const f2 e1 = mk2(lo(mag) - dgt[0][c], hi(mag) - dgt[1][c]), e2 = mk2(lo(mag) - dgi[0][c], hi(mag) - dgi[1][c]);
+                l3 = fma2(e1, e1, l3);
+                l4 = fma2(e2, e2, l4);
+                const f2 gm = mul2(fma2(kIsc, e2, mul2(kIs, e1)), ir);         // zero off the interior
+                gxy[c] = mul2(gm, sx[c]);
+                gxy[6 + c] = mul2(gm, sy[c]);
+            }
+            lossacc[3] = fmaf(lo(l3), lo(mI), fmaf(hi(l3), hi(mI), lossacc[3]));
+            lossacc[4] = fmaf(lo(l4), lo(mI), fmaf(hi(l4), hi(mI), lossacc[4]));
+            store_pairs(s_G2, gxy, 12);
         }
         __syncthreads();   // (X2) Sobel gradients visible
 
         // ---------------- stage C: Sobel adjoint into G, then A^T G ----------------
         if (warp == 0 && lane < NFETCH && k + 1 < n) stash(cur ^ 1, lane, nxt);     // visible after barrier (R2)
         {
-            float Gs[2][6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) { Gs[0][c] = lo(G[c]); Gs[1][c] = hi(G[c]); }
+            for (int di = -1; di <= 1; ++di)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (valid[s]) {
-#pragma unroll
-                    for (int di = -1; di <= 1; ++di)
-#pragma unroll
-                        for (int dj = -1; dj <= 1; ++dj) {
-                            if (di == 0 && dj == 0) continue;
-                            const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
-                            const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
-                            const int qn = qg[s] + di * RG + dj;
-                            if (wx != 0.0f) {
-                                const float4 ga = s_gxa[qn];
-                                const float2 gb = s_gxb[qn];
-                                const float gv[6] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y};
-#pragma unroll
-                                for (int c = 0; c < 6; ++c) Gs[s][c] = fmaf(wx, gv[c], Gs[s][c]);
-                            }
-                            if (wy != 0.0f) {
-                                const float4 ga = s_gya[qn];
-                                const float2 gb = s_gyb[qn];
-                                const float gv[6] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y};
-#pragma unroll
-                                for (int c = 0; c < 6; ++c) Gs[s][c] = fmaf(wy, gv[c], Gs[s][c]);
-                            }
-                        }
+                for (int dj = -1; dj <= 1; ++dj) {
+                    if (di == 0 && dj == 0) continue;
+                    const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
+                    const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
+                    const float4* pn = s_G2 + (tid + HALO + di * R + dj);
+                    if (wx != 0.0f) {
+                        const float4 v0 = pn[0], v1 = pn[NE], v2 = pn[2 * NE];
+                        G[0] = fma2(bc2(wx), mk2(v0.x, v0.y), G[0]); G[1] = fma2(bc2(wx), mk2(v0.z, v0.w), G[1]);
+                        G[2] = fma2(bc2(wx), mk2(v1.x, v1.y), G[2]); G[3] = fma2(bc2(wx), mk2(v1.z, v1.w), G[3]);
+                        G[4] = fma2(bc2(wx), mk2(v2.x, v2.y), G[4]); G[5] = fma2(bc2(wx), mk2(v2.z, v2.w), G[5]);
+                    }
+                    if (wy != 0.0f) {
+                        const float4 v0 = pn[3 * NE], v1 = pn[4 * NE], v2 = pn[5 * NE];
+                        G[0] = fma2(bc2(wy), mk2(v0.x, v0.y), G[0]); G[1] = fma2(bc2(wy), mk2(v0.z, v0.w), G[1]);
+                        G[2] = fma2(bc2(wy), mk2(v1.x, v1.y), G[2]); G[3] = fma2(bc2(wy), mk2(v1.z, v1.w), G[3]);
+                        G[4] = fma2(bc2(wy), mk2(v2.x, v2.y), G[4]); G[5] = fma2(bc2(wy), mk2(v2.z, v2.w), G[5]);
+                    }
                 }
-            }
-#pragma unroll
-            for (int c = 0; c < 6; ++c) G[c] = mk2(Gs[0][c], Gs[1][c]);
             f2 sums[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) sums[i] = bc2(0.0f);
