@@ -114,16 +114,6 @@ BE_HD void be_boundary_backward1(float d1, float d2, float lb, float glb, float*
     *gd1 = a; *gd2 = b;
 }
 
-// one edge of be_wedge_backward for one pixel: contributions (gd, ga) of dL/d|D| routed through D = a<0 ? sign(d) r : d
-BE_HD void be_edge_backward1(float d, float a, float absD, float sgw, float w2, float* gd, float* ga) {
-    if (a < 0.0f) {
-        const float ir = (absD > 0.0f) ? be_rcp(absD) : 0.0f;
-        *gd = sgw * d * ir; *ga = sgw * w2 * a * ir;
-    } else {
-        *gd = sgw * be_sign(d); *ga = 0.0f;
-    }
-}
-
 // be_wedge_backward for two pixels; acc[0..3] are packed partial sums (vertex x, vertex y, angle A, angle B)
 BE_HD void be_wedge_backward2(const BePatch& P, int k, f2 X, f2 Y, float w, f2 g, f2* acc) {
     const f2 dx = sub2(X, bc2(P.vx[k])), dy = sub2(Y, bc2(P.vy[k]));
@@ -133,7 +123,9 @@ BE_HD void be_wedge_backward2(const BePatch& P, int k, f2 X, f2 Y, float w, f2 g
     const f2 dB = fma2(bc2(csB), dy, mul2(bc2(-snB), dx)), aB = fma2(bc2(csB), dx, mul2(bc2(snB), dy));
     const f2 awA = mul2(aA, bc2(w)), awB = mul2(aB, bc2(w));
     const f2 cA2 = fma2(dA, dA, mul2(awA, awA)), cB2 = fma2(dB, dB, mul2(awB, awB));
-    float gdA[2], gaA[2], gdB[2], gaB[2];
+    // Per edge: D = a<0 ? sign(d) r : d.  d|D|/dd = d/|D| on both branches (sign(d) = d/|d| where |D| = |d|), d|D|/da = w^2 a/|D| on the
+    // cap branch only; 1/|D| from MUFU.RCP, 0 at |D| = 0 (abs'(0) = 0).
+    float sA[2], sB[2], irA[2], irB[2], mA[2], mB[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const float dAs = s ? hi(dA) : lo(dA), aAs = s ? hi(aA) : lo(aA), dBs = s ? hi(dB) : lo(dB), aBs = s ? hi(aB) : lo(aB);
@@ -143,11 +135,14 @@ BE_HD void be_wedge_backward2(const BePatch& P, int k, f2 X, f2 Y, float w, f2 g
         const bool in = (k == 0) ? ((f * DA > 0.0f) && (f * DB < 0.0f)) : ((f * DA >= 0.0f) && (f * DB <= 0.0f));
         const float sg = (s ? hi(g) : lo(g)) * (in ? f : -f);
         const float absA = fabsf(DA), absB = fabsf(DB);
-        const float wA = (absA < absB) ? 1.0f : ((absA == absB) ? 0.5f : 0.0f);
-        be_edge_backward1(dAs, aAs, absA, sg * wA, w * w, &gdA[s], &gaA[s]);
-        be_edge_backward1(dBs, aBs, absB, sg * (1.0f - wA), w * w, &gdB[s], &gaB[s]);
+        const float wA = (absA < absB) ? 1.0f : ((absA == absB) ? 0.5f : 0.0f);      // min(): ties split 1/2
+        sA[s] = sg * wA; sB[s] = sg * (1.0f - wA);
+        irA[s] = (absA > 0.0f) ? be_rcp(absA) : 0.0f; irB[s] = (absB > 0.0f) ? be_rcp(absB) : 0.0f;
+        mA[s] = (aAs < 0.0f) ? w * w : 0.0f; mB[s] = (aBs < 0.0f) ? w * w : 0.0f;
     }
-    const f2 GdA = mk2(gdA[0], gdA[1]), GaA = mk2(gaA[0], gaA[1]), GdB = mk2(gdB[0], gdB[1]), GaB = mk2(gaB[0], gaB[1]);
+    const f2 tA = mul2(mk2(sA[0], sA[1]), mk2(irA[0], irA[1])), tB = mul2(mk2(sB[0], sB[1]), mk2(irB[0], irB[1]));
+    const f2 GdA = mul2(tA, dA), GaA = mul2(mul2(tA, mk2(mA[0], mA[1])), aA);
+    const f2 GdB = mul2(tB, dB), GaB = mul2(mul2(tB, mk2(mB[0], mB[1])), aB);
     // acc[0] += (gdA snA - gaA csA) + (gdB snB - gaB csB)
     acc[0] = add2(acc[0], add2(fma2(GdA, bc2(snA), mul2(GaA, bc2(-csA))), fma2(GdB, bc2(snB), mul2(GaB, bc2(-csB)))));
     // acc[1] += (-gdA csA - gaA snA) + (-gdB csB - gaB snB)
