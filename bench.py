@@ -10,7 +10,7 @@ processes its own batch of pairs (weak scaling, no data-path collective); time =
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
 C-ABI entry point with H2D/D2H copies inside the timed region, `roofline` the HBM roofline of the dominant kernel
-(be_run2_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
+(be_run3_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
 `--impl reference` times the CPU port of the reference's eager PyTorch path (the reference itself is Python and is
 not present on the GPU box; oracle/be_oracle.py is pinned to it by tests/golden)."""
 from __future__ import annotations
@@ -38,12 +38,12 @@ UNIT = 'patches/s'
 # algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
 # params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
 ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
-# dram__bytes_read.sum + dram__bytes_write.sum of be_run2_kernel<INFER> for one 64-pair launch, from the committed
-# `ncu --set full` capture profiles/r1b_run2_kernel_full.txt (155.3 MB + 37.9 MB); None for other batch sizes
-TRAFFIC_NCU_64 = 155.325440e6 + 37.926400e6
+# dram__bytes_read.sum + dram__bytes_write.sum of be_run3_kernel<INFER> for one 64-pair launch, from the committed
+# `ncu --set full` capture profiles/r1f_run3_kernel_full.txt; None for other batch sizes
+TRAFFIC_NCU_64 = None
 TRAFFIC_NCU = None
-# warp-instructions per patch of be_run2_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1c_run2_kernel_full.txt)
-WARP_INST_PER_PATCH = 6406.0
+# warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1f_run3_kernel_full.txt)
+WARP_INST_PER_PATCH = 4726.0
 SM_COUNT, SMSP_PER_SM = 148, 4
 
 
@@ -199,6 +199,23 @@ def extra_configs(args, rank, world, dev, barrier):
     ms = _timed(train_step, steps, 3, dev, barrier, world)
     out['train_step'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss, configs[2])', 'value': Bt * L * world / (ms / 1e3), 'unit': UNIT,
                          'ms_per_step': ms, 'pairs_per_gpu': Bt, 'collective': '8-byte mask-count all-reduce between the two loss stages'}
+    # the same step with the whole batch of configs[2] (32 pairs) on every GPU: throughput of the kernels once the GPU is full
+    Bt2 = 32
+    targs.batch_size = Bt2
+    crit2 = GlobalLossFused(targs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
+    crit2.update_gamma()
+    raw2 = synth.raw_global(Bt2, L, seed=330 + rank).to(dev).requires_grad_(True)
+    img2 = synth.image_pairs(Bt2, S, S, seed=331 + rank).to(dev)
+    gt2, bd2, deri2, zg2 = [t.to(dev) for t in synth.loss_targets(Bt2, S, S, seed=332 + rank)]
+
+    def train_step2():
+        raw2.grad = None
+        crit2(raw2, img2, gt2, bd2, deri2, zg2).backward()
+
+    ms = _timed(train_step2, steps, 3, dev, barrier, world)
+    out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
+                             'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2}
+    del crit2, raw2, img2, gt2, bd2, deri2, zg2
     # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
@@ -309,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
                    'api': 'be_host_render_fold (pinned host buffers, synchronous)'},
            'gpu_launches': int(launches),
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                        'traffic': TRAFFIC_NCU, 'kernel': 'be_run2_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
+                        'traffic': TRAFFIC_NCU, 'kernel': 'be_run3_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
                         'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
                         'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
                                 'see profiles/ for pipe utilisation'},

@@ -35,7 +35,7 @@ int fail(const char* fmt, ...) {
 
 }  // namespace
 
-constexpr int BE_HOST_CHUNKS = 8;   // pipeline depth of the host-buffer entry point
+constexpr int BE_HOST_CHUNKS = 16;  // maximum pipeline depth of the host-buffer entry point
 
 struct be_ctx {
     be_config cfg;
@@ -281,6 +281,34 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     return 0;
 }
 
+// pass B on pairs [b0, b0+B) of the context's workspace (records and accumulator are per pair, so disjoint ranges may be in
+// flight on different streams)
+static int render_fold_range(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
+                             int b0, int32_t B, int32_t densify_w, float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry,
+                             float* dev_depth, float* dev_conf, float* dev_depth_thr, cudaStream_t st, bool tm) {
+    const BeGeom& g = c->g;
+    const int L = g.Hp * g.Wp;
+    float* table = c->table + (size_t)b0 * L * BE_REC;
+    float* acc = c->acc + (size_t)b0 * g.H * g.W * BE_ACC;
+    if (tm) cudaEventRecord(c->ev[0], st);
+    BE_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * g.H * g.W * BE_ACC * sizeof(float), st));
+    if (tm) cudaEventRecord(c->ev[1], st);
+    be_launch_setup(dev_est, param_mode, B * L, c->cam, table, nullptr, st);
+    if (tm) cudaEventRecord(c->ev[2], st);
+    BeRunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = table; a.img = make_img(dev_img, layout); a.acc = acc;
+    a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
+    pick_runs(g, B, &a.G, &a.runs_per_row);
+    launch_run(BE_RUN_INFER, a, st);
+    if (tm) cudaEventRecord(c->ev[3], st);
+    const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
+    be_launch_normalise(acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
+    if (tm) cudaEventRecord(c->ev[4], st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
                        int32_t B, int32_t densify_w, float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry,
                        float* dev_depth, float* dev_conf, float* dev_depth_thr, void* stream) {
@@ -289,29 +317,9 @@ int be_render_fold_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, cons
     BE_REQUIRE(dev_est && dev_img && dev_image && dev_sharp && dev_refoc && dev_bndry && dev_depth && dev_conf, "null pointer");
     BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_render_fold_fwd takes 12-parameter patches");
     BE_REQUIRE(B >= 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
-    if (B == 0) return 0;
     if (ensure_acc(c)) return 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    const BeGeom& g = c->g;
-    const int L = g.Hp * g.Wp;
-    const bool tm = c->timing != 0;
-    if (tm) cudaEventRecord(c->ev[0], st);
-    BE_CUDA(cudaMemsetAsync(c->acc, 0, (size_t)B * g.H * g.W * BE_ACC * sizeof(float), st));
-    if (tm) cudaEventRecord(c->ev[1], st);
-    be_launch_setup(dev_est, param_mode, B * L, c->cam, c->table, nullptr, st);
-    if (tm) cudaEventRecord(c->ev[2], st);
-    BeRunArgs a;
-    memset(&a, 0, sizeof(a));
-    a.table = c->table; a.img = make_img(dev_img, layout); a.acc = c->acc;
-    a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, B, &a.G, &a.runs_per_row);
-    launch_run(BE_RUN_INFER, a, st);
-    if (tm) cudaEventRecord(c->ev[3], st);
-    const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
-    be_launch_normalise(c->acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
-    if (tm) cudaEventRecord(c->ev[4], st);
-    BE_CUDA(cudaGetLastError());
-    return 0;
+    return render_fold_range(c, dev_est, param_mode, dev_img, layout, 0, B, densify_w, dev_image, dev_sharp, dev_refoc, dev_bndry,
+                             dev_depth, dev_conf, dev_depth_thr, (cudaStream_t)stream, c->timing != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -673,34 +681,68 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
         BE_CUDA(cudaMalloc(&c->st_out, mb * 16 * HW * sizeof(float)));
         c->st_bytes = mb * (L * 12 + 22 * HW) * sizeof(float);
     }
-    // Software pipeline over chunks of pairs: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three streams, so that
-    // the PCIe transfers (the larger part of an end-to-end call) hide behind the renderer.
-    cudaStream_t s_in = c->st_streams[0], s_k = c->st_streams[1], s_out = c->st_streams[2];
-    const int nchunk = B < BE_HOST_CHUNKS ? B : BE_HOST_CHUNKS;
+    // Software pipeline over chunks of pairs: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three streams, so that the
+    // PCIe transfers hide behind the renderer.  Measured on the B200 box (tools/microbench/pcie.py, BE_HOST_TRACE=1): the call is
+    // bound by the link, not by the kernels - D2H runs at 50 GB/s alone but at 21-32 GB/s while H2D is active.  Alternatives tried
+    // and rejected: two alternating kernel streams (no gain), an export kernel writing the maps straight into the pinned host
+    // arrays (52 GB/s alone, tools/microbench/zerocopy.cu, but 20 % slower in the pipeline than the copy engine).
+    if (ensure_acc(c)) return 1;
+    cudaStream_t s_in = c->st_streams[0], s_out = c->st_streams[2];
+    // Chunk sizes ramp up and down again (1:2:3:4:3:2:1): a small first chunk starts the kernels early, a small last chunk
+    // leaves little D2H after the last kernel, the large middle chunks run the renderer at full-wave efficiency.
+    static const int ramp_on = [] { const char* e = getenv("BE_HOST_RAMP"); return e ? atoi(e) : 1; }();
+    static const int want = [] { const char* e = getenv("BE_HOST_CHUNKS"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : (v > BE_HOST_CHUNKS ? BE_HOST_CHUNKS : v); }();
+    int bounds[BE_HOST_CHUNKS + 1];
+    int nchunk = B < want ? B : want;
+    if (ramp_on && B >= 16) {
+        static const int wgt[7] = {1, 2, 3, 4, 3, 2, 1};
+        nchunk = 7;
+        int acc_w = 0;
+        bounds[0] = 0;
+        for (int i = 0; i < 7; ++i) { acc_w += wgt[i]; bounds[i + 1] = (int)((long long)B * acc_w / 16); }
+    } else {
+        for (int i = 0; i <= nchunk; ++i) bounds[i] = (int)((long long)B * i / nchunk);
+    }
     const size_t f = sizeof(float);
     float* o = c->st_out;
     float* d_map[7] = {o, o + (size_t)B * 6 * HW, o + (size_t)B * 9 * HW, o + (size_t)B * 12 * HW, o + (size_t)B * 13 * HW,
                        o + (size_t)B * 14 * HW, o + (size_t)B * 15 * HW};
     float* h_map[7] = {image, sharp, refoc, bndry, depth, conf, depth_thr};
     const size_t per[7] = {6 * HW, 3 * HW, 3 * HW, HW, HW, HW, HW};
+    static const bool trace = getenv("BE_HOST_TRACE") != nullptr;
+    static cudaEvent_t tev[3 * BE_HOST_CHUNKS + 1];
+    if (trace && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(tev[3 * BE_HOST_CHUNKS], s_in);
     for (int i = 0; i < nchunk; ++i) {
-        const int b0 = (int)((long long)B * i / nchunk), b1 = (int)((long long)B * (i + 1) / nchunk), nb = b1 - b0;
+        const int b0 = bounds[i], b1 = bounds[i + 1], nb = b1 - b0;
+        cudaStream_t s_k = c->st_streams[1];
         BE_CUDA(cudaMemcpyAsync(c->st_est + (size_t)b0 * L * 12, est + (size_t)b0 * L * 12, (size_t)nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaMemcpyAsync(c->st_img + (size_t)b0 * 6 * HW, img + (size_t)b0 * 6 * HW, (size_t)nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaEventRecord(c->st_events[2 * i], s_in));
+        if (trace) cudaEventRecord(tev[3 * i], s_in);
         BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[2 * i], 0));
-        if (be_render_fold_fwd(c, c->st_est + (size_t)b0 * L * 12, param_mode, c->st_img + (size_t)b0 * 6 * HW, layout, nb, densify_w,
-                               d_map[0] + b0 * per[0], d_map[1] + b0 * per[1], d_map[2] + b0 * per[2], d_map[3] + b0 * per[3],
-                               d_map[4] + b0 * per[4], d_map[5] + b0 * per[5], d_map[6] + b0 * per[6], (void*)s_k))
+        if (render_fold_range(c, c->st_est + (size_t)b0 * L * 12, param_mode, c->st_img + (size_t)b0 * 6 * HW, layout, b0, nb, densify_w,
+                              d_map[0] + b0 * per[0], d_map[1] + b0 * per[1], d_map[2] + b0 * per[2], d_map[3] + b0 * per[3],
+                              d_map[4] + b0 * per[4], d_map[5] + b0 * per[5], d_map[6] + b0 * per[6], s_k, false))
             return 1;
         BE_CUDA(cudaEventRecord(c->st_events[2 * i + 1], s_k));
+        if (trace) cudaEventRecord(tev[3 * i + 1], s_k);
         BE_CUDA(cudaStreamWaitEvent(s_out, c->st_events[2 * i + 1], 0));
         for (int m = 0; m < 7; ++m) {
             if (!h_map[m]) continue;
             BE_CUDA(cudaMemcpyAsync(h_map[m] + b0 * per[m], d_map[m] + b0 * per[m], nb * per[m] * f, cudaMemcpyDeviceToHost, s_out));
         }
+        if (trace) cudaEventRecord(tev[3 * i + 2], s_out);
     }
+    BE_CUDA(cudaGetLastError());
     BE_CUDA(cudaStreamSynchronize(s_out));
+    if (trace) {
+        for (int i = 0; i < nchunk; ++i) {
+            float a, b2, d;
+            cudaEventElapsedTime(&a, tev[3 * BE_HOST_CHUNKS], tev[3 * i]); cudaEventElapsedTime(&b2, tev[3 * BE_HOST_CHUNKS], tev[3 * i + 1]); cudaEventElapsedTime(&d, tev[3 * BE_HOST_CHUNKS], tev[3 * i + 2]);
+            fprintf(stderr, "chunk %d: h2d done %.3f  kernels done %.3f  d2h done %.3f\n", i, a, b2, d);
+        }
+    }
     return 0;
 }
 

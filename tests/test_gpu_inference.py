@@ -141,6 +141,29 @@ def test_host_buffer_entry_point_equals_device_entry_point():
     host = ctx.host_render_fold(est.pin_memory(), img.pin_memory(), _lib.planar_layout(S, S))
     for d, h in zip(dev, host):
         assert relmax(h.numpy(), d.numpy()) < 2e-6
+    # pageable output arrays take the cudaMemcpyAsync route instead of the export kernel: same bits
+    pageable = [torch.full_like(h, float('nan')).clone() for h in host]
+    assert not any(t.is_pinned() for t in pageable)
+    ctx.host_render_fold(est, img, _lib.planar_layout(S, S), out=pageable)
+    for p, h in zip(pageable, host):
+        assert relmax(p.numpy(), h.numpy()) < 2e-6      # the fold's reduction order differs from call to call
+
+
+@pytest.mark.parametrize('B', [8, 11])
+def test_host_buffer_entry_point_chunked_pipeline(B):
+    """More pairs than pipeline chunks (8): exercises both kernel streams, the 16-byte (B=8) and the scalar (B=11, odd
+    chunk sizes) forms of the export kernel, and repeated calls into the same pinned outputs."""
+    from blurry_edges_b200 import _lib
+    S = GEOMS['tiny']
+    g = geom(S)
+    est = O.restore_global(synth.raw_global(B, g.L, seed=91))
+    img = planar_pair(synth.image_pairs(B, S, S, seed=92))
+    ctx = _ctx(S, max_batch=B)
+    dev = _run_b(ctx, est, img)
+    host = ctx.host_render_fold(est.pin_memory(), img.pin_memory(), _lib.planar_layout(S, S))
+    host = ctx.host_render_fold(est.pin_memory(), img.pin_memory(), _lib.planar_layout(S, S), out=host)
+    for d, h in zip(dev, host):
+        assert relmax(h.numpy(), d.numpy()) < 2e-6
 
 
 def test_batch64_full_size_properties():
