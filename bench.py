@@ -40,7 +40,7 @@ UNIT = 'patches/s'
 ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
 # dram__bytes_read.sum + dram__bytes_write.sum of be_run3_kernel<INFER> for one 64-pair launch, from the committed
 # `ncu --set full` capture profiles/r1f_run3_kernel_full.txt; None for other batch sizes
-TRAFFIC_NCU_64 = None
+TRAFFIC_NCU_64 = 155.291904e6 + 38.151424e6
 TRAFFIC_NCU = None
 # warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1f_run3_kernel_full.txt)
 WARP_INST_PER_PATCH = 4726.0
@@ -335,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
                         'achieved_ginst_per_s': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / 1e9,
                         'peak_ginst_per_s': SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) / 1e3,
                         'frac': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / (SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) * 1e6)},
-           'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run_kernel': shares[2], 'be_normalise_kernel': shares[3]},
+           'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run3_kernel': shares[2], 'be_normalise_kernel': shares[3]},
            'clocks': clk.summary(), 'wall_s_timed_region': t_wall}
     res.update(extra)
     if world == 1 and not args.no_cpu:

@@ -18,6 +18,19 @@ def _cam_cfg(args, H, W, stride, max_batch=1):
                             max_batch=max_batch)
 
 
+def _adjugate3(A):
+    """adj(A) of [...,3,3] matrices by cofactors (device tensor ops, differentiable).  The reference builds it from A^2 and
+    traces (utils/postprocessing_loss.py:127-128,148-149), which loses ~3e-3 in fp32; `inverse_3by3`
+    here does not go through it (one kernel, fp64 cofactors), the method exists for subclasses that call it directly."""
+    a, b, c = A[..., 0, 0], A[..., 0, 1], A[..., 0, 2]
+    d, e, f = A[..., 1, 0], A[..., 1, 1], A[..., 1, 2]
+    g, h, i = A[..., 2, 0], A[..., 2, 1], A[..., 2, 2]
+    rows = [torch.stack([e * i - f * h, c * h - b * i, b * f - c * e], -1),
+            torch.stack([f * g - d * i, a * i - c * g, c * d - a * f], -1),
+            torch.stack([d * h - e * g, b * g - a * h, a * e - b * d], -1)]
+    return torch.stack(rows, -2)
+
+
 class DepthEtas:
     """utils/depth_etas.py:3-37"""
 
@@ -109,7 +122,7 @@ class PostProcessLocalBase(PostProcessBase):
         return xx.view(1, self.R, self.R).to(self.device), yy.view(1, self.R, self.R).to(self.device)
 
     def get_adjA(self, A, A2, trA, trA2):
-        raise NotImplementedError('inverse_3by3 is a single kernel here; the trace-formula adjugate of the reference is not exposed')
+        return _adjugate3(A)
 
 
 class PostProcessGlobalBase(PostProcessBase):
@@ -132,7 +145,7 @@ class PostProcessGlobalBase(PostProcessBase):
         return xx.view(1, self.R, self.R, 1, 1).to(self.device), yy.view(1, self.R, self.R, 1, 1).to(self.device)
 
     def get_adjA(self, A, A2, trA, trA2):
-        raise NotImplementedError('inverse_3by3 is a single kernel here; the trace-formula adjugate of the reference is not exposed')
+        return _adjugate3(A)
 
     def _fold(self, patches, planes, mode=0):
         return ops.Fold.apply(patches, self._be, planes, self.H, self.W, mode)

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libblurry_edges_b200.so')
-SOURCES = ['be_kernels.cu', 'be_run2.cu', 'be_run3.cu', 'be_train.cu', 'be_loss2.cu', 'be_ops.cu', 'be_capi.cu']
+SOURCES = ['be_kernels.cu', 'be_run3.cu', 'be_train.cu', 'be_loss2.cu', 'be_ops.cu', 'be_capi.cu']
 HEADERS = ['be_math.cuh', 'be_pack.cuh', 'be_internal.h', os.path.join('..', '..', 'include', 'blurry_edges_b200.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v']

@@ -130,13 +130,7 @@ int validate_cfg(const be_config* cfg) {
     return 0;
 }
 
-// BE_RUN_V=1|2 select the earlier generations of the renderer (A/B measurements only)
-void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) {
-    static const int v = [] { const char* e = getenv("BE_RUN_V"); return e ? atoi(e) : 3; }();
-    if (v == 1) be_launch_run(mode, a, st);
-    else if (v == 2) be_launch_run2(mode, a, st);
-    else be_launch_run3(mode, a, st);
-}
+void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) { be_launch_run3(mode, a, st); }
 
 // Split every patch row into `runs` runs of G consecutive patches (one CTA each).  Long runs amortise the sliding-window
 // state (pixel loads, accumulator flushes) best; small batches need shorter runs to fill the 148 SMs (3 CTAs each) a few
@@ -365,7 +359,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.crec = c->crec;
     a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
     pick_runs(g, B, &a.G, &a.runs_per_row);
-    be_launch_run3(BE_RUN_TRAINFWD, a, st);   // the loss kernel needs the colour records only this generation writes
+    launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
     BE_CUDA(cudaGetLastError());
@@ -397,8 +391,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     a.kc = (float)(gammas7[0] / norm[0]); a.kcc = (float)(gammas7[1] / norm[1]); a.kbc = (float)(gammas7[2] / norm[2]);
     a.ks = (float)(gammas7[3] / norm[3]); a.ksc = (float)(gammas7[4] / norm[4]); a.kbl = (float)(gammas7[5] / norm[5]);
     a.gamma_d = (float)gammas7[6];
-    static const int v = [] { const char* e = getenv("BE_LOSS_V"); return e ? atoi(e) : 2; }();   // 1: first-generation kernel (A/B runs)
-    if (v == 1) be_launch_loss(false, a, st); else be_launch_loss2(a, st);
+    be_launch_loss2(a, st);
     be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -429,7 +422,7 @@ int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, cons
     sc.scale[0] = 1.0 / (RR * Np); sc.scale[1] = 1.0 / (RR * Np); sc.scale[2] = 1.0 / (Ri2 * Np);
     sc.gamma[0] = 1.0f; sc.gamma[1] = (float)beta_bndry_loc; sc.gamma[2] = (float)beta_smthns;
     a.kc = (float)sc.scale[0]; a.kbl = (float)(beta_bndry_loc * sc.scale[1]); a.ks = (float)(beta_smthns * sc.scale[2]);
-    be_launch_loss(true, a, st);
+    be_launch_loss(a, st);
     be_launch_loss_reduce(c->partials, B, sc, nullptr, dev_terms, dev_loss, st);
     BE_CUDA(cudaGetLastError());
     return 0;

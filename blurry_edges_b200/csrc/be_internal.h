@@ -77,13 +77,11 @@ void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& 
 void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st);
 void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
                           const float* bndry_depth, float* T, cudaStream_t st);
-void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st);   // first generation; the local-stage loss
+void be_launch_loss(const BeLossArgs& a, cudaStream_t st);               // local-stage loss (be_train.cu)
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
 void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
                            float* loss, cudaStream_t st);
-void be_launch_run(int mode, const BeRunArgs& a, cudaStream_t st);    // first generation (kept for A/B checks)
-void be_launch_run2(int mode, const BeRunArgs& a, cudaStream_t st);   // warp-specialised, shared-memory slots (A/B checks)
-void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // + packed fp32x2 slots: the hot-path renderer
+void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // renderer + fused fold (be_run3.cu)
 void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st);
 void be_launch_refold(const float* unfolded, const BeGeom& g, int M, float* image, cudaStream_t st);

@@ -18,7 +18,6 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NT = BE_THREADS;               // 224 threads, 7 warps, two pixel slots per thread
-constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
 constexpr int HALO = BE_MAX_R + 1;
 constexpr int NE = NT + 2 * HALO;
 

@@ -1,17 +1,16 @@
 // sm_100a kernels of the TRAINING side: global-stage loss (global_training.py:62-157) and local-stage loss
 // (local_training.py:32-52), forward + analytic backward, plus the small kernels between the two passes.
 //
-//   be_run_kernel<TRAINFWD>   (be_kernels.cu) renders both images + boundary and folds them -> accumulator [B,H,W,8],
+//   be_run3_kernel<TRAINFWD>  (be_run3.cu) renders both images + boundary and folds them -> accumulator [B,H,W,8],
 //                             counts the depth-term mask.
 //   be_train_normalise_kernel accumulator -> global image / boundary (detached targets, :154-155), written into the
 //                             packed per-pixel target record T[B,H,W,36] and, optionally, as planar tensors.
 //   be_train_pack_kernel      fills the rest of T: noisy + ground-truth pixels, log2(bndry_dist+1), z_gt, the
 //                             ground-truth derivative and Sobel(global image) (:106-110,117-118,123-124), so that the
 //                             loss kernel fetches everything about one pixel with nine 16-byte loads.
-//   be_loss_kernel<LOCAL>     one CTA walks a run of patches; per patch: phase 1 + ridge solve, render, direct dL/dP,
-//                             Sobel forward + adjoint through shared memory, A^T G + second solve, per-pixel backward to
-//                             the 14 per-patch sums, chain rule to the 12 (10) raw parameters.  Three warp-transposing
-//                             reductions per patch; no unfolded tensor, no autograd graph.
+//   be_local_loss_kernel      local-stage loss: one CTA per patch; phase 1 + ridge solve, render, direct dL/dP, Sobel forward
+//                             + adjoint through shared memory, A^T G + second solve, per-pixel backward to the per-patch
+//                             sums, chain rule to the 10 raw parameters.  (The global-stage loss is be_loss2.cu.)
 //   be_loss_reduce_kernel     per-CTA partial sums -> the seven loss terms and the weighted loss.
 #include "be_internal.h"
 
@@ -118,9 +117,8 @@ struct Slot {
     bool valid, interior;
 };
 
-template <bool LOCAL>
-__global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
-    constexpr int NIMG = LOCAL ? 1 : 2;
+__global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
+    constexpr int NIMG = 1;
     constexpr int NCH = 3 * NIMG;
     constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
 
@@ -146,9 +144,8 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
     const int b = blk / g.Hp;
     const int px0 = run * a.G;
     const int n = min(a.G, g.Wp - px0);
-    const int y0 = py * g.stride;
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
-    const int np = LOCAL ? 10 : 12;
+    const int np = 10;
 
     if (tid < R) s_axis[tid] = be_axis(tid, R);
     if (tid < 8) reinterpret_cast<float4*>(s_rec[0])[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
@@ -172,14 +169,11 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
     __syncthreads();
     const float Y[2] = {s_axis[sl[0].i], s_axis[sl[1].i]};
     const float X[2] = {s_axis[sl[0].j], s_axis[sl[1].j]};
-    const float kd = LOCAL ? 0.0f : a.gamma_d / (float)(*a.mask_count);
-    const size_t TPS = (size_t)a.NB * g.H * g.W * 4;      // floats between consecutive float4 planes of T
 
     float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     for (int k = 0; k < n; ++k) {
         const int cur = k & 1;
-        const int x0 = (px0 + k) * g.stride;
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
         if (warp == 0 && k + 1 < n) {
             if (lane < 8) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 1) * BE_REC) + lane);
@@ -195,20 +189,9 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
             P.flip[0] = r3.x; P.flip[1] = r3.y; P.z[0] = r3.z; P.z[1] = r3.w;
             P.inv_eta[0] = r4.x; P.inv_eta[1] = r4.y; P.inv_eta[2] = r4.z; P.inv_eta[3] = r4.w;
         }
-        // per-slot target pointers
-        const float* tp[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-            tp[s] = LOCAL ? nullptr : a.T + (((size_t)b * g.H + y0 + sl[s].i) * g.W + x0 + sl[s].j) * 4;   // plane 0 of this pixel
         auto ld_ny = [&](int s, float* y) {
-            if (LOCAL) {
-                const float* p = a.l_ny + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
-                y[0] = __ldg(p); y[1] = __ldg(p + 1); y[2] = __ldg(p + 2);
-            } else {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
-                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS));
-                y[0] = q0.x; y[1] = q0.y; y[2] = q0.z; y[3] = q0.w; y[4] = q1.x; y[5] = q1.y;
-            }
+            const float* p = a.l_ny + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
+            y[0] = __ldg(p); y[1] = __ldg(p + 1); y[2] = __ldg(p + 2);
         };
 
         // ---------------- stage 1: phase 1 ----------------
@@ -274,7 +257,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) C[q] = s_col[q];
         float G[2][NCH];
-        float gbv[2] = {0.f, 0.f}, bdv[2] = {0.f, 0.f};
+        float bdv[2] = {0.f, 0.f};
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (sl[s].valid) {
@@ -288,7 +271,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                 }
                 s_Pa[sl[s].q] = make_float4(Pv[0], Pv[1], Pv[2], Pv[3]);
                 s_Pb[sl[s].q] = make_float2(Pv[4], Pv[5]);
-                if (LOCAL) {
+                {
                     const float* p = a.l_gt + (((size_t)b * R + sl[s].i) * R + sl[s].j) * 3;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -297,21 +280,6 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                         G[s][c] = 2.0f * a.kc * e1;
                     }
                     bdv[s] = __ldg(a.l_bd + ((size_t)b * R + sl[s].i) * R + sl[s].j);
-                } else {
-                    const float2 t1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS + 2));
-                    const float4 t2 = __ldg(reinterpret_cast<const float4*>(tp[s] + 2 * TPS));
-                    const float4 t3 = __ldg(reinterpret_cast<const float4*>(tp[s] + 3 * TPS));
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp[s] + 4 * TPS));
-                    const float gt[6] = {t1.x, t1.y, t2.x, t2.y, t2.z, t2.w};
-                    const float gi[6] = {t3.x, t3.y, t3.z, t3.w, t4.x, t4.y};
-                    gbv[s] = t4.z; bdv[s] = t4.w;
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        const float e1 = Pv[c] - gt[c], e2 = Pv[c] - gi[c];
-                        lossacc[0] = fmaf(e1, e1, lossacc[0]);
-                        lossacc[1] = fmaf(e2, e2, lossacc[1]);
-                        G[s][c] = 2.0f * (a.kc * e1 + a.kcc * e2);
-                    }
                 }
             }
         }
@@ -339,16 +307,10 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                             if (wy != 0.0f) sy[c] = fmaf(wy, pv[c], sy[c]);
                         }
                     }
-                float dgt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dgi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (LOCAL) {
+                float dgt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                {
                     const float* p = a.l_deri + (((size_t)b * (R - 2) + sl[s].i - 1) * (R - 2) + sl[s].j - 1) * 3;
                     dgt[0] = __ldg(p); dgt[1] = __ldg(p + 1); dgt[2] = __ldg(p + 2);
-                } else {
-                    const float4 t6 = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
-                    const float4 t7 = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
-                    const float4 t8 = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
-                    dgt[0] = t6.x; dgt[1] = t6.y; dgt[2] = t6.z; dgt[3] = t6.w; dgt[4] = t7.x; dgt[5] = t7.y;
-                    dgi[0] = t7.z; dgi[1] = t7.w; dgi[2] = t8.x; dgi[3] = t8.y; dgi[4] = t8.z; dgi[5] = t8.w;
                 }
                 float gx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gy[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -358,12 +320,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                     const float mag = v * ir;
                     const float e1 = mag - dgt[c];
                     lossacc[3] = fmaf(e1, e1, lossacc[3]);
-                    float gm = 2.0f * a.ks * e1;
-                    if (!LOCAL) {
-                        const float e2 = mag - dgi[c];
-                        lossacc[4] = fmaf(e2, e2, lossacc[4]);
-                        gm = fmaf(2.0f * a.ksc, e2, gm);
-                    }
+                    const float gm = 2.0f * a.ks * e1;
                     gx[c] = gm * sx[c] * ir;
                     gy[c] = gm * sy[c] * ir;
                 }
@@ -478,20 +435,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                     const float lb = be_boundary(d1[s], d2[s]);
                     const float bl = bdv[s] * lb;
                     lossacc[5] = fmaf(bl, bl, lossacc[5]);
-                    float glb = 2.0f * a.kbl * bdv[s] * bl;
-                    if (!LOCAL) {
-                        const float e = lb - gbv[s];
-                        lossacc[2] = fmaf(e, e, lossacc[2]);
-                        glb = fmaf(2.0f * a.kbc, e, glb);
-                        const float zgv = __ldg(tp[s] + 5 * TPS);
-                        const int mk = be_mask(d1[s], d2[s], false);
-                        if (zgv != 0.0f && mk != 0) {
-                            const float e2 = ((mk == 1) ? P.z[0] : P.z[1]) - zgv;
-                            lossacc[6] = fmaf(e2, e2, lossacc[6]);
-                            if (mk == 1) sums[12] = fmaf(2.0f * kd, e2, sums[12]);
-                            else sums[13] = fmaf(2.0f * kd, e2, sums[13]);
-                        }
-                    }
+                    const float glb = 2.0f * a.kbl * bdv[s] * bl;
                     be_boundary_backward(d1[s], d2[s], lb, glb, &gd1, &gd2);
                     be_wedge_backward(P, 0, X[s], Y[s], g.w, gd1, &sums[0]);
                     be_wedge_backward(P, 1, X[s], Y[s], g.w, gd2, &sums[4]);
@@ -518,14 +462,7 @@ __global__ void __maxnreg__(128) be_loss_kernel(const BeLossArgs a) {
                 const float xs = gr[8], as = gr[9];
                 out[0] = xs * S[0]; out[1] = xs * S[1]; out[2] = xs * S[4]; out[3] = xs * S[5];
                 out[4] = as * (S[2] + S[3]); out[5] = as * S[3]; out[6] = as * (S[6] + S[7]); out[7] = as * S[7];
-                if (LOCAL) {
-                    out[8] = S[8] * gr[0]; out[9] = S[9] * gr[1];
-                } else {
-                    out[8] = (S[8] + S[12] * gr[4]) * gr[0];
-                    out[9] = (S[9] + S[13] * gr[6]) * gr[1];
-                    out[10] = (S[10] + S[12] * gr[5]) * gr[2];
-                    out[11] = (S[11] + S[13] * gr[7]) * gr[3];
-                }
+                out[8] = S[8] * gr[0]; out[9] = S[9] * gr[1];
             }
         }
     }
@@ -594,10 +531,9 @@ void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const flo
     ++g_be_launches;
 }
 
-void be_launch_loss(bool local, const BeLossArgs& a, cudaStream_t st) {
+void be_launch_loss(const BeLossArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    if (local) be_loss_kernel<true><<<grid, BE_THREADS, 0, st>>>(a);
-    else be_loss_kernel<false><<<grid, BE_THREADS, 0, st>>>(a);
+    be_local_loss_kernel<<<grid, BE_THREADS, 0, st>>>(a);
     ++g_be_launches;
 }
 

@@ -182,7 +182,7 @@ int be_eval_depth(be_ctx* ctx, const float* dev_depth, const float* dev_gt, int6
 
 /* Measurement hook: with timing enabled, be_render_fold_fwd brackets each of its four device operations with CUDA
  * events on the caller's stream; be_ctx_last_timing waits for the last call and returns their durations in ms:
- * ms4 = {accumulator memset, be_setup_kernel, be_run_kernel, be_normalise_kernel}. */
+ * ms4 = {accumulator memset, be_setup_kernel, be_run3_kernel, be_normalise_kernel}. */
 int be_ctx_set_timing(be_ctx* ctx, int32_t enable);
 int be_ctx_last_timing(be_ctx* ctx, float* ms4);
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../blurry_edges_b200/csrc/be_math.cuh"
+#include "../blurry_edges_b200/csrc/be_pack.cuh"
 
 namespace {
 
@@ -413,6 +414,49 @@ int behm_global_loss(const float* raw, const float* img_ny, const float* img_gt,
         *loss = (float)l;
     }
     return 0;
+}
+
+// Packed (two-pixel) functions of be_pack.cuh against the scalar specification of be_math.cuh, on n random pixels of one
+// patch.  out[0..3]: max |difference| of (d1, d2), h, boundary, mask weights (bit-identical arithmetic: expected 0);
+// out[4]: max relative difference of the wedge backward sums (algebraically rewritten: d/|D| instead of sign(d)).
+void hm_pack_selfcheck(const float* p12, const float* cam7, const float* xy, int n, float w, float* out5) {
+    const BeCam cam = make_cam(cam7);
+    BePatch P;
+    be_patch_setup(p12, BE_PARAMS_RESTORED12, cam, P);
+    for (int k = 0; k < 5; ++k) out5[k] = 0.0f;
+    float acc_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    f2 acc_p[8];
+    for (int k = 0; k < 8; ++k) acc_p[k] = bc2(0.0f);
+    for (int i = 0; i + 1 < n; i += 2) {
+        const float X0 = xy[2 * i], Y0 = xy[2 * i + 1], X1 = xy[2 * i + 2], Y1 = xy[2 * i + 3];
+        float a1, a2, b1, b2;
+        be_pixel_dists(P, X0, Y0, w, &a1, &a2);
+        be_pixel_dists(P, X1, Y1, w, &b1, &b2);
+        f2 d1, d2;
+        be_pixel_dists2(P, mk2(X0, X1), mk2(Y0, Y1), w, &d1, &d2);
+        out5[0] = fmaxf(out5[0], fmaxf(fmaxf(fabsf(lo(d1) - a1), fabsf(hi(d1) - b1)), fmaxf(fabsf(lo(d2) - a2), fabsf(hi(d2) - b2))));
+        for (int q = 0; q < 4; ++q) {
+            const f2 h = be_h2((q & 1) ? d2 : d1, P.inv_eta[q]);
+            out5[1] = fmaxf(out5[1], fmaxf(fabsf(lo(h) - be_h((q & 1) ? a2 : a1, P.inv_eta[q])), fabsf(hi(h) - be_h((q & 1) ? b2 : b1, P.inv_eta[q]))));
+        }
+        const f2 lb = be_boundary2(d1, d2);
+        out5[2] = fmaxf(out5[2], fmaxf(fabsf(lo(lb) - be_boundary(a1, a2)), fabsf(hi(lb) - be_boundary(b1, b2))));
+        for (int dw = 0; dw < 2; ++dw) {
+            float m1, m2;
+            be_mask_weights(a1, a2, dw != 0, &m1, &m2);
+            const int mk = be_mask(a1, a2, dw != 0);
+            out5[3] = fmaxf(out5[3], fabsf(m1 - (mk == 1 ? 1.0f : 0.0f)) + fabsf(m2 - (mk == 2 ? 1.0f : 0.0f)));
+        }
+        const float g0 = 0.3f + 0.01f * (float)(i % 7), g1 = -0.2f + 0.02f * (float)(i % 5);
+        for (int k = 0; k < 2; ++k) {
+            be_wedge_backward(P, k, X0, Y0, w, g0, &acc_s[4 * k]);
+            be_wedge_backward(P, k, X1, Y1, w, g1, &acc_s[4 * k]);
+            be_wedge_backward2(P, k, mk2(X0, X1), mk2(Y0, Y1), w, mk2(g0, g1), &acc_p[4 * k]);
+        }
+    }
+    float num = 0.0f, den = 1e-30f;
+    for (int k = 0; k < 8; ++k) { num = fmaxf(num, fabsf(lo(acc_p[k]) + hi(acc_p[k]) - acc_s[k])); den = fmaxf(den, fabsf(acc_s[k])); }
+    out5[4] = num / den;
 }
 
 }  // extern "C"

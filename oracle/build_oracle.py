@@ -9,12 +9,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, '_build', 'libbe_hostmath.so')
 SRC = os.path.join(HERE, 'be_hostmath.cpp')
-DEP = os.path.join(HERE, '..', 'blurry_edges_b200', 'csrc', 'be_math.cuh')
+DEPS = [os.path.join(HERE, '..', 'blurry_edges_b200', 'csrc', f) for f in ('be_math.cuh', 'be_pack.cuh')]
 
 
 def build(force=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > max(os.path.getmtime(SRC), os.path.getmtime(DEP)):
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) > max(os.path.getmtime(f) for f in [SRC] + DEPS):
         return OUT
     cmd = ['g++', '-O2', '-std=c++17', '-fopenmp', '-fPIC', '-shared', '-x', 'c++', SRC, '-o', OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -87,3 +87,12 @@ def local_loss(est, img_ny, gt_img, bndry_dist, deri, betas, g: O.Geometry, cam:
                                 _p(dummy), _p(dummy))
     assert rc == 0
     return float(loss[0]), terms[:3], grad
+
+
+def pack_selfcheck(params12, cam: O.Camera, xy, w=1.0, rho_prime=10.39):
+    """Packed two-pixel functions (be_pack.cuh) vs the scalar specification (be_math.cuh) on the pixel positions xy [n,2]
+    of one patch with restored parameters params12 -> 5 error figures (see hm_pack_selfcheck)."""
+    p, xy = _f(params12), _f(xy)
+    out = np.zeros(5, dtype=np.float32)
+    lib().hm_pack_selfcheck(_p(p), _p(_cam7(cam, rho_prime)), _p(xy), C.c_int(xy.shape[0]), C.c_float(w), _p(out))
+    return out

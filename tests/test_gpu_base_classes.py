@@ -102,6 +102,11 @@ def test_inverse_sobel_depth(gbase):
     A = synth.uniform((2, 5, 5, 3, 3), 21, -1.0, 1.0)
     A = A @ A.transpose(-1, -2) + 4.86 * torch.eye(3)
     _both(gbase.inverse_3by3, O.inv3_sym, [A])
+    # get_adjA(A, A2, trA, trA2) (utils/postprocessing_loss.py:127-128,148-149): adj(A) = det(A) A^-1
+    Ad = A.double()
+    adj = gbase.get_adjA(A.cuda(), None, None, None).cpu().double()
+    ref = torch.linalg.det(Ad)[..., None, None] * torch.linalg.inv(Ad)
+    assert float((adj - ref).abs().max() / ref.abs().max()) < 1e-5
     _both(gbase.get_image_derivative, O.sobel_mag, [synth.uniform((4, 3, 21, 21), 22)])
     _both(gbase.get_image_derivative, O.sobel_mag, [synth.uniform((2, 3, 45, 45), 23)])
     cal = DepthEtas(_args(45), 'cuda:0')

@@ -88,3 +88,18 @@ def test_local_loss_forward_backward(betas, eta_lo):
         (g32,) = torch.autograd.grad(O.local_loss(e32, ny, gt, bd, deri, betas, g), e32)
         floor, _ = _grad_err(g32.numpy(), gref.numpy())
         assert emax < max(2e-5, 2 * floor), (emax, floor)
+
+
+@pytest.mark.parametrize('seed,scale', [(0, 0.1), (1, 1.0), (2, 1.0)])
+def test_packed_two_pixel_functions_equal_the_scalar_specification(seed, scale):
+    """be_pack.cuh (FFMA2 halves on the GPU, plain fp32 pairs on the host) against be_math.cuh: the forward functions are the
+    same IEEE operations in the same order (bit-identical), the wedge backward is algebraically rewritten (1e-5 relative)."""
+    g = O.Geometry(H=21, W=21)
+    raw = synth.raw_global(1, 1, seed=40 + seed) * (scale / 0.1)
+    p = O.restore_global(raw)[0, 0].numpy()
+    rng = np.random.default_rng(seed)
+    xy = np.concatenate([np.stack(np.meshgrid(np.linspace(-1, 1, 21), np.linspace(-1, 1, 21)), -1).reshape(-1, 2),
+                         rng.uniform(-1, 1, size=(559, 2))]).astype(np.float32)
+    err = hostmath.pack_selfcheck(p, O.Camera(), xy)
+    assert err[0] == 0.0 and err[1] == 0.0 and err[2] == 0.0 and err[3] == 0.0, err
+    assert err[4] < 1e-5, err
