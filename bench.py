@@ -38,6 +38,8 @@ UNIT = 'patches/s'
 # algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
 # params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
 ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
+# the same with pixels sourced from the unfolded [2,3,R,R,Hp,Wp] tensor the reference signature hands in (SURVEY.md 8d "bytes_api")
+API_BYTES_PER_PATCH = 48.0 + 2 * 3 * R * R * 4 + 15 * S * S * 4 / L
 # dram__bytes_read.sum + dram__bytes_write.sum of be_run3_kernel<INFER> for one 64-pair launch, from the committed
 # `ncu --set full` capture profiles/r1f_run3_kernel_full.txt; None for other batch sizes
 TRAFFIC_NCU_64 = 155.291904e6 + 38.151424e6
@@ -216,6 +218,25 @@ def extra_configs(args, rank, world, dev, barrier):
     out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
                              'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2}
     del crit2, raw2, img2, gt2, bd2, deri2, zg2
+    # ---- the Smish activation of LocalStage, an HBM-bound elementwise kernel (8 B/element fwd, 12 B/element bwd) ----
+    from blurry_edges_b200 import smish
+    xs = torch.rand(8192, 64, R, R, device=dev) * 8 - 4            # one LocalStage activation of 4096 patches x 2 images: 925 MB
+    gs = torch.rand_like(xs)
+    ms_f = _timed(lambda: smish(xs), steps, 3, dev, barrier, world)
+    xg = xs.clone().requires_grad_(True)
+
+    def smish_fb():
+        xg.grad = None
+        smish(xg).backward(gs)
+
+    ms_fb = _timed(smish_fb, steps, 3, dev, barrier, world)
+    hbm, _ = peaks()
+    nb = xs.numel() * 4
+    out['smish'] = {'metric': 'Smish activation (models/local_stage.py:4-6), fused elementwise kernel', 'elements': xs.numel(),
+                    'fwd_ms': ms_f, 'fwd_gbs': 2 * nb / (ms_f / 1e3) / 1e9, 'fwd_frac_of_hbm_peak': 2 * nb / (ms_f / 1e3) / 1e9 / hbm,
+                    'fwd_bwd_ms': ms_fb, 'bwd_gbs': 3 * nb / ((ms_fb - ms_f) / 1e3) / 1e9,
+                    'note': 'working set 1.85 GB >> L2; bwd figure = 3 arrays / (fwd+bwd - fwd) time, includes autograd glue'}
+    del xs, gs, xg
     # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
@@ -328,6 +349,7 @@ def run_ours(args, rank, world, local_rank):
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                         'traffic': TRAFFIC_NCU, 'kernel': 'be_run3_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
                         'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
+                        'frac_if_pixels_came_unfolded': API_BYTES_PER_PATCH * B * L / (run_ms / 1e3) / 1e9 / peak,
                         'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
                                 'see profiles/ for pipe utilisation'},
            'sm_issue': {'note': 'binding resource of the fused kernel: warp-instruction issue slots (1 per SMSP per clock)',
@@ -355,6 +377,23 @@ def run_ours(args, rank, world, local_rank):
                                                     'note': 'oracle/be_hostmath.cpp: the kernels\' arithmetic on host cores, OpenMP over pairs'}
         except Exception as e:  # the C port is optional evidence
             res['cpu_baseline']['c_port_openmp'] = {'error': str(e)[:100]}
+        try:   # the reference's eager op chain on this same B200 (the oracle port on cuda:0, one pair per call)
+            from oracle import be_oracle as O
+            g, cam = O.Geometry(H=S, W=S), O.Camera()
+            e3, i3 = make_inputs(2, seed=902)
+            e3, i3 = e3.to(dev), i3.to(dev)
+            with torch.no_grad(), torch.device(dev):     # the oracle's constants (grids, ridge) are made on the default device
+                O.inference(e3[:1], i3[:1], g, cam, 10.39, None, trace_form=True)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for b in range(2):
+                    O.inference(e3[b:b + 1], i3[b:b + 1], g, cam, 10.39, None, trace_form=True)
+                torch.cuda.synchronize(dev)
+            res['cpu_baseline']['eager_port_on_this_gpu'] = {'value': 2 * L / (time.perf_counter() - t0), 'unit': UNIT,
+                                                             'note': 'the same torch restatement of the reference run eagerly on cuda:0 (fp32, '
+                                                                     'one pair per call): the launch/HBM-bound path the fused kernels replace'}
+        except Exception as e:
+            res['cpu_baseline']['eager_port_on_this_gpu'] = {'error': str(e)[:100]}
     print(json.dumps(res), flush=True)
 
 

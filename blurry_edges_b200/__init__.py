@@ -10,5 +10,6 @@ from .fused import PostProcessFused, PostProcessLocalFused
 from .pipeline import DepthEstimatorFused
 from .losses import GlobalLossFused, LocalLossFused
 from .big import BigImageFused, block_windows, shard_blocks
+from .activations import SmishFused, patch_reference_smish, smish
 
-__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'DepthEstimatorFused', 'block_windows', 'shard_blocks', '_lib']
+__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'DepthEstimatorFused', 'block_windows', 'shard_blocks', 'SmishFused', 'patch_reference_smish', 'smish', '_lib']

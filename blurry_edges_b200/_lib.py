@@ -63,6 +63,8 @@ _SIGS = {
     'be_dists2indicators_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P]),
     'be_elementwise': (C.c_int, [_P, C.c_int32, _P, C.c_double, C.c_int64, _P, _P]),
     'be_elementwise_bwd': (C.c_int, [_P, C.c_int32, _P, _P, C.c_double, C.c_int64, _P, _P]),
+    'be_smish': (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    'be_smish_bwd': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     'be_etas2depth': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     'be_etas2depth_bwd': (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
     'be_inverse_3by3': (C.c_int, [_P, _P, C.c_int64, _P, _P]),

@@ -574,6 +574,18 @@ int be_elementwise_bwd(be_ctx* c, int32_t op, const float* dev_x, const float* d
     BE_CUDA(cudaGetLastError());
     return 0;
 }
+int be_smish(be_ctx* c, const float* dev_x, int64_t n_, float* dev_y, void* stream) {
+    BE_OP_PROLOGUE(dev_x && dev_y)
+    be_op_smish(dev_x, (size_t)n_, dev_y, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+int be_smish_bwd(be_ctx* c, const float* dev_x, const float* dev_grad_y, int64_t n_, float* dev_grad_x, void* stream) {
+    BE_OP_PROLOGUE(dev_x && dev_grad_y && dev_grad_x)
+    be_op_smish_bwd(dev_x, dev_grad_y, (size_t)n_, dev_grad_x, st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
 int be_etas2depth(be_ctx* c, const float* dev_eta1, const float* dev_eta2, int64_t n_, float* dev_z, void* stream) {
     BE_OP_PROLOGUE(dev_eta1 && dev_eta2 && dev_z)
     be_op_depth(dev_eta1, dev_eta2, c->cam, (size_t)n_, dev_z, st);

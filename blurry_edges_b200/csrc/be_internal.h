@@ -97,6 +97,8 @@ void be_op_indicators_bwd(const float* dists, const float* etas, const float* gw
                           cudaStream_t st);
 void be_op_unary(int op, const float* x, float p0, const BeCam& cam, size_t n, float* y, cudaStream_t st);
 void be_op_unary_bwd(int op, const float* x, const float* gy, float p0, const BeCam& cam, size_t n, float* gx, cudaStream_t st);
+void be_op_smish(const float* x, size_t n, float* y, cudaStream_t st);
+void be_op_smish_bwd(const float* x, const float* gy, size_t n, float* gx, cudaStream_t st);
 void be_op_depth(const float* e1, const float* e2, const BeCam& cam, size_t n, float* z, cudaStream_t st);
 void be_op_depth_bwd(const float* e1, const float* e2, const float* gz, const BeCam& cam, size_t n, float* g1, float* g2, cudaStream_t st);
 void be_op_inverse3(const float* A, size_t n, float* out, cudaStream_t st);

@@ -141,6 +141,46 @@ __global__ void __launch_bounds__(TPB) k_unary_bwd(int op, const float* __restri
     gx[i] = r;
 }
 
+// ---- Smish activation of LocalStage (models/local_stage.py:4-6): y = x tanh(log(1 + sigmoid(x))) ------------------------------
+// With t = 1 + sigmoid(x): tanh(log t) = (t^2 - 1)/(t^2 + 1).  HBM bound (8 B/element forward, 12 B/element backward): 16-byte
+// loads and stores, streaming cache hints, grid-stride over a grid sized to the SM count.
+__device__ __forceinline__ float smish_f(float x, float* dfdx) {
+    const float s = be_rcp(1.0f + be_exp2(-x * 1.44269504f));
+    const float t = 1.0f + s, t2 = t * t;
+    const float r = be_rcp(t2 + 1.0f);
+    if (dfdx) *dfdx = 4.0f * t * r * r * s * (1.0f - s);
+    return (t2 - 1.0f) * r;
+}
+
+__global__ void __launch_bounds__(TPB) k_smish(const float* __restrict__ x, size_t n, float* __restrict__ y, int vec4) {
+    const size_t stride = (size_t)gridDim.x * TPB;
+    if (vec4) {
+        for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < n / 4; i += stride) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+            float4 r;
+            r.x = v.x * smish_f(v.x, nullptr); r.y = v.y * smish_f(v.y, nullptr);
+            r.z = v.z * smish_f(v.z, nullptr); r.w = v.w * smish_f(v.w, nullptr);
+            __stcs(reinterpret_cast<float4*>(y) + i, r);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) y[i] = x[i] * smish_f(x[i], nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_smish_bwd(const float* __restrict__ x, const float* __restrict__ gy, size_t n,
+                                                   float* __restrict__ gx, int vec4) {
+    const size_t stride = (size_t)gridDim.x * TPB;
+    auto one = [](float v, float g) { float d; const float f = smish_f(v, &d); return g * fmaf(v, d, f); };
+    if (vec4) {
+        for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < n / 4; i += stride) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i), g = __ldcs(reinterpret_cast<const float4*>(gy) + i);
+            __stcs(reinterpret_cast<float4*>(gx) + i, make_float4(one(v.x, g.x), one(v.y, g.y), one(v.z, g.z), one(v.w, g.w)));
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * TPB + threadIdx.x; i < n; i += stride) gx[i] = one(x[i], gy[i]);
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_depth(const float* __restrict__ e1, const float* __restrict__ e2, BeCam cam, size_t n,
                                                float* __restrict__ z) {
     const size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
@@ -318,6 +358,18 @@ void be_op_unary(int op, const float* x, float p0, const BeCam& cam, size_t n, f
 }
 void be_op_unary_bwd(int op, const float* x, const float* gy, float p0, const BeCam& cam, size_t n, float* gx, cudaStream_t st) {
     k_unary_bwd<<<blocks_for(n), TPB, 0, st>>>(op, x, gy, p0, cam, n, gx); ++g_be_launches;
+}
+static unsigned smish_grid(size_t work) {   // a few CTAs per SM, grid-stride inside
+    const size_t want = (work + TPB - 1) / TPB, cap = 148 * 16;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+void be_op_smish(const float* x, size_t n, float* y, cudaStream_t st) {
+    const int v4 = (n % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0);
+    k_smish<<<smish_grid(v4 ? n / 4 : n), TPB, 0, st>>>(x, n, y, v4); ++g_be_launches;
+}
+void be_op_smish_bwd(const float* x, const float* gy, size_t n, float* gx, cudaStream_t st) {
+    const int v4 = (n % 4 == 0) && (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)gx) % 16 == 0);
+    k_smish_bwd<<<smish_grid(v4 ? n / 4 : n), TPB, 0, st>>>(x, gy, n, gx, v4); ++g_be_launches;
 }
 void be_op_depth(const float* e1, const float* e2, const BeCam& cam, size_t n, float* z, cudaStream_t st) {
     k_depth<<<blocks_for(n), TPB, 0, st>>>(e1, e2, cam, n, z); ++g_be_launches;

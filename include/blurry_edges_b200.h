@@ -147,7 +147,9 @@ int be_local_loss(be_ctx* ctx, const float* dev_est, const float* dev_img_ny, co
  *   be_image_derivative    :114-117   n planes [n,H,W] -> [n,H-2,W-2]
  *   be_fold                :151-164   n planes of patches [n,R,R,Hp,Wp] -> [n,H,W]; mode 0 divides by num_patches, 1 = plain sum
  *   be_fold_depth          :166-173   depth_map fp32 + depth_mask int32 [n,R,R,Hp,Wp] -> depth, confidence [n,H,W]
- *   be_unfold              nn.Unfold  n planes [n,H,W] -> [n,R,R,Hp,Wp]; mode 0 = adjoint of be_fold mode 0, 1 = plain */
+ *   be_unfold              nn.Unfold  n planes [n,H,W] -> [n,R,R,Hp,Wp]; mode 0 = adjoint of be_fold mode 0, 1 = plain
+ *   be_smish               models/local_stage.py:4-6  Smish activation x tanh(log(1 + sigmoid(x))) of the LocalStage CNN, n elements
+ *                          (the elementwise op next to the hot path) */
 int be_params2dists(be_ctx* ctx, const float* dev_params, int32_t K, int32_t B, int64_t Lsp, float* dev_dists, void* stream);
 int be_params2dists_bwd(be_ctx* ctx, const float* dev_params, int32_t K, const float* dev_grad_dists, int32_t B, int64_t Lsp,
                         float* dev_grad_params, void* stream);
@@ -157,6 +159,8 @@ int be_dists2indicators_bwd(be_ctx* ctx, const float* dev_dists, const float* de
 int be_elementwise(be_ctx* ctx, int32_t op, const float* dev_x, double p0, int64_t n, float* dev_y, void* stream);
 int be_elementwise_bwd(be_ctx* ctx, int32_t op, const float* dev_x, const float* dev_grad_y, double p0, int64_t n, float* dev_grad_x,
                        void* stream);
+int be_smish(be_ctx* ctx, const float* dev_x, int64_t n, float* dev_y, void* stream);
+int be_smish_bwd(be_ctx* ctx, const float* dev_x, const float* dev_grad_y, int64_t n, float* dev_grad_x, void* stream);
 int be_etas2depth(be_ctx* ctx, const float* dev_eta1, const float* dev_eta2, int64_t n, float* dev_z, void* stream);
 int be_etas2depth_bwd(be_ctx* ctx, const float* dev_eta1, const float* dev_eta2, const float* dev_grad_z, int64_t n, float* dev_g1,
                       float* dev_g2, void* stream);

@@ -54,3 +54,17 @@ def test_script_subclass_reaches_our_constructor_and_fails_loudly(shim):
         bt.PostProcess(args, None, torch.device('cpu'))
     with pytest.raises(be.BlurryEdgesError, match='CUDA'):
         bt.DepthEtas(args, torch.device('cpu'))
+
+
+def test_patch_reference_smish_swaps_the_class():
+    """activations.patch_reference_smish replaces models.local_stage.Smish (models/local_stage.py:4-6); a LocalStage built
+    afterwards holds SmishFused modules."""
+    ls = refimport.module('models.local_stage')
+    from blurry_edges_b200 import SmishFused, patch_reference_smish
+    orig = patch_reference_smish(ls)
+    try:
+        net = ls.LocalStage()
+        acts = [m for m in net.modules() if isinstance(m, SmishFused)]
+        assert len(acts) > 0 and not any(isinstance(m, orig) for m in net.modules())
+    finally:
+        ls.Smish = orig
