@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
                             'sample': f'{pairs} pairs/step x {args.steps} steps, torch {torch.__version__} eager fp32 CPU, '
                                       'oracle/be_oracle.py restatement of the reference (one pair per call, as the reference helper)'},
            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(out), flush=True)
+    _emit(out)
 
 
 def _timed(fn, steps, warmup, dev, barrier, world):
@@ -394,10 +394,27 @@ def run_ours(args, rank, world, local_rank):
                                                                      'one pair per call): the launch/HBM-bound path the fused kernels replace'}
         except Exception as e:
             res['cpu_baseline']['eager_port_on_this_gpu'] = {'error': str(e)[:100]}
-    print(json.dumps(res), flush=True)
+    _emit(res)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(obj):
+    """The ONE JSON line, on the real stdout (everything else, e.g. NCCL's version banner, was redirected to stderr)."""
+    line = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)      # libraries (NCCL) print to fd 1: keep stdout for the JSON line only
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
