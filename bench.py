@@ -97,10 +97,16 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def restore_params(raw):
+    """The script glue between GlobalStage and the helper (blurry_edges_test.py:135-138): xy*3, angles wrapped to [0,2pi),
+    eta coefficients + 0.5.  Input synthesis only; written here so that the product arm never imports oracle/."""
+    import math
+    return torch.cat([raw[..., :4] * 3, torch.remainder((raw[..., 4:8] + 1) * math.pi, 2 * math.pi), raw[..., 8:] + 0.5], dim=-1)
+
+
 def make_inputs(B, seed):
     import synth
-    from oracle import be_oracle as O   # only restore_global(): builds the synthetic parameters, not the measured path
-    est = O.restore_global(synth.raw_global(B, L, seed=seed)).contiguous()
+    est = restore_params(synth.raw_global(B, L, seed=seed)).contiguous()
     img = synth.image_pairs(B, S, S, seed=seed + 1).permute(0, 1, 4, 2, 3).contiguous()   # planar [B,2,3,H,W]
     return est, img
 
@@ -177,7 +183,6 @@ def extra_configs(args, rank, world, dev, barrier):
     import argparse as ap
     import synth
     from blurry_edges_b200 import BigImageFused, GlobalLossFused, PostProcessFused, shard_blocks
-    from oracle import be_oracle as O   # input synthesis only (restore_global)
     import torch.distributed as dist
     cam = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
     base = dict(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=cam)
@@ -241,7 +246,7 @@ def extra_configs(args, rank, world, dev, barrier):
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
     helper = PostProcessFused(pargs, None, dev, as_numpy=False)
-    est_w = O.restore_global(synth.raw_global(Bw, L, seed=310 + rank)).to(dev)
+    est_w = restore_params(synth.raw_global(Bw, L, seed=310 + rank)).to(dev)
     img_w = synth.image_pairs(Bw, S, S, seed=311 + rank).to(dev)
     ms = _timed(lambda: helper(est_w, img_w, colors_only=False), steps, 3, dev, barrier, world)
     out['dense_w'] = {'metric': "patches/sec pass B, --densify 'w' (configs[4])", 'value': Bw * L * world / (ms / 1e3), 'unit': UNIT,
@@ -251,7 +256,7 @@ def extra_configs(args, rank, world, dev, barrier):
     bargs = ap.Namespace(batch_size=1, big_img_size=[big, big], n_margin_patch=10, densify=None, **base)
     bh = BigImageFused(bargs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
     lo, hi = shard_blocks(bh.nblk, rank, world)
-    est_b = O.restore_global(synth.raw_global(hi - lo, L, seed=320 + rank)).to(dev)
+    est_b = restore_params(synth.raw_global(hi - lo, L, seed=320 + rank)).to(dev)
     big_img = (torch.from_numpy(synth.photon_pairs(1, big, big, seed=321)).float() / 190.0).permute(0, 1, 4, 2, 3)[0].contiguous().to(dev)
     ms = _timed(lambda: bh(est_b, big_img), steps, 3, dev, barrier, world)
     npatch_big = ((big - R) // STRIDE + 1) ** 2
