@@ -132,19 +132,29 @@ int validate_cfg(const be_config* cfg) {
 
 void launch_run(int mode, const BeRunArgs& a, cudaStream_t st) { be_launch_run3(mode, a, st); }
 
-// Split every patch row into `runs` runs of G consecutive patches (one CTA each).  Long runs amortise the sliding-window
-// state (pixel loads, accumulator flushes) best; small batches need shorter runs to fill the 148 SMs (3 CTAs each) a few
-// times over.  Runs never get shorter than 8 patches, never longer than 96.
-int pick_runs(const BeGeom& g, int items, int* G, int* runs) {
-    const int maxG = 96, minG = 8, target_ctas = 148 * 3 * 3;
-    int r = (g.Wp + maxG - 1) / maxG;
-    const long long rows = (long long)items * g.Hp;
-    while ((long long)r * rows < target_ctas && (g.Wp + r) / (r + 1) >= minG) ++r;
-    *runs = r;
-    *G = (g.Wp + r - 1) / r;
-    *runs = (g.Wp + *G - 1) / *G;
+// Split every patch row into `runs` runs of G consecutive patches (one CTA each).  Long runs amortise the per-CTA start-up
+// (pixel loads, pipeline fill, the final flush of all 441 accumulators: ~`ovh` patch-times); but the grid runs in waves of 148 * ctas_per_sm CTAs and
+// a partly filled last wave costs a whole one, which matters for small batches and for the chunks of the host pipeline.  Pick the
+// split that minimises  waves * (G + ovh)  over runs of 8..96 patches.
+int pick_runs(const BeGeom& g, int items, int ctas_per_sm, double ovh, int* G, int* runs) {
+    const int maxG = 96, minG = 8;
+    const long long rows = (long long)items * g.Hp, slots = 148LL * ctas_per_sm;
+    double best = 1e300;
+    int bestG = g.Wp < maxG ? g.Wp : maxG;
+    for (int r = (g.Wp + maxG - 1) / maxG; r <= g.Wp; ++r) {
+        const int Gr = (g.Wp + r - 1) / r;
+        if (Gr < minG && r > 1) break;
+        const int rr = (g.Wp + Gr - 1) / Gr;
+        const long long waves = (rows * rr + slots - 1) / slots;
+        const double cost = (double)waves * (Gr + ovh);
+        if (cost < best * 0.999) { best = cost; bestG = Gr; }
+    }
+    *G = bestG;
+    *runs = (g.Wp + bestG - 1) / bestG;
     return 0;
 }
+constexpr int RUN_CTAS = 3, LOSS_CTAS = 2;        // resident CTAs per SM of be_run3_kernel / be_loss2_kernel
+constexpr double RUN_OVH = 5.0, LOSS_OVH = 1.0;   // calibrated: G=64 vs G=32 at 64 pairs differ by 1.9 % (be_run3)
 
 }  // namespace
 
@@ -269,7 +279,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
     a.g = c->g; a.cam = c->cam; a.NB = M; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, M, &a.G, &a.runs_per_row);
+    pick_runs(c->g, M, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -293,7 +303,7 @@ static int render_fold_range(be_ctx* c, const float* dev_est, int32_t param_mode
     memset(&a, 0, sizeof(a));
     a.table = table; a.img = make_img(dev_img, layout); a.acc = acc;
     a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, B, &a.G, &a.runs_per_row);
+    pick_runs(g, B, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_INFER, a, st);
     if (tm) cudaEventRecord(c->ev[3], st);
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
@@ -358,7 +368,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
     a.crec = c->crec;
     a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, B, &a.G, &a.runs_per_row);
+    pick_runs(g, B, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
@@ -382,7 +392,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     a.table = c->table; a.gtable = c->gtable; a.crec = c->crec; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
     a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
     a.g = g; a.NB = B;
-    pick_runs(g, B, &a.G, &a.runs_per_row);
+    pick_runs(g, B, LOSS_CTAS, LOSS_OVH, &a.G, &a.runs_per_row);
     BeLossScale sc;
     memset(&sc, 0, sizeof(sc));
     sc.nterms = 7;
@@ -471,7 +481,7 @@ int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, co
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors; a.blocks = c->blk_dev;
     a.g = c->g; a.cam = c->cam; a.NB = nitem; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, nitem, &a.G, &a.runs_per_row);
+    pick_runs(c->g, nitem, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -496,7 +506,7 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc; a.blocks = c->blk_dev;
     a.g = g; a.cam = c->cam; a.NB = nblk; a.densify_w = densify_w; a.accH = acc_H; a.accW = acc_W;
-    pick_runs(g, nblk, &a.G, &a.runs_per_row);
+    pick_runs(g, nblk, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_INFER, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
