@@ -221,3 +221,22 @@ def test_precal_local_colors_vs_oracle_and_golden():
     assert col.shape == (40, 3, 3)
     assert relmax(col, O.colors_local(est.to(F64), pat.to(F64), g).numpy()) < 1e-5
     assert relmax(col, Golden('inference')('precal/f64')) < 1e-5
+
+
+def test_repeatability_full_size_stress():
+    """The warp-specialised renderer hands data between warps through named barriers, an mbarrier and cp.async; a protocol slip
+    would show up as rare, run-dependent corruption.  20 launches on the same 64-pair batch must agree with the first to within the
+    reordering noise of the floating-point reductions (the fold's atomics), and the discrete depth count exactly."""
+    S, B = 147, 64
+    g = geom(S)
+    est = O.restore_global(synth.raw_global(B, g.L, seed=85)).cuda()
+    img = planar_pair(synth.image_pairs(B, S, S, seed=86)).cuda()
+    ctx = _ctx(S, max_batch=B)
+    from blurry_edges_b200 import _lib
+    lay = _lib.planar_layout(S, S)
+    first = [o.clone() for o in ctx.render_fold(est, img, lay)]
+    for _ in range(20):
+        again = ctx.render_fold(est, img, lay)
+        for name, a, b in zip(MAPS, first, again):
+            err = float((a - b).abs().max() / a.abs().max())
+            assert err < (1e-6 if name != 'conf' else 1e-7), (name, err)

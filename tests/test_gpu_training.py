@@ -183,3 +183,22 @@ def test_local_loss_vs_oracle_and_golden(name):
     for ref in (g64.numpy(), gl(f'lloss/{name}/f64/grad')):
         emax, _ = _grad_err(grad, ref)
         assert emax < max(2e-5, 2 * floor), (emax, floor)         # eta reaches 1.6e-3 in this fixture: fp32 noise floor applies
+
+
+def test_training_repeatability_full_size_stress():
+    """Same idea for the loss kernels (three CTA barriers per patch, double-buffered records, a rotating chain-rule warp): 8 repeated
+    32-pair steps give the same loss (fp64 final reduction, fixed order: bit-identical up to the fold's atomics) and gradients."""
+    from blurry_edges_b200 import GlobalLossFused
+    S, B = 147, 32
+    g = geom(S)
+    crit = GlobalLossFused(_gargs(S, B), None, 'cuda:0')
+    crit.update_gamma()
+    raw = synth.raw_global(B, g.L, seed=300)
+    img = synth.image_pairs(B, S, S, seed=301)
+    gt, bd, deri, zg = synth.loss_targets(B, S, S, seed=302)
+    l0, g0, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
+    assert np.isfinite(l0) and np.isfinite(g0).all()
+    for _ in range(8):
+        l1, g1, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
+        assert abs(l1 - l0) <= 1e-6 * abs(l0)
+        assert float(np.abs(g1 - g0).max()) <= 2e-6 * float(np.abs(g0).max())
