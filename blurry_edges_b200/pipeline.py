@@ -1,7 +1,8 @@
 """The inference driver body of the reference (blurry_edges_test.depth_estimator, blurry_edges_test.py:114-149) with every
 step that is not a network on this library's kernels: patch gather -> LocalStage -> pass A (+ angle wrap) -> pm assembly ->
 GlobalStage -> pass B (restore inside the kernel) -> confidence threshold -> depth metrics.  The two networks stay stock
-PyTorch modules supplied by the caller."""
+PyTorch modules supplied by the caller.  With `cuda_graph=True` the whole body (networks included) is captured once per input
+shape into a CUDA graph and replayed: at the reference's batch size of 1 the body is launch bound."""
 from __future__ import annotations
 
 import torch
@@ -12,8 +13,10 @@ from .fused import _geometry_from_args
 
 
 class DepthEstimatorFused(nn.Module):
-    def __init__(self, args, local_module, global_module, device='cuda:0', max_batch=None):
+    def __init__(self, args, local_module, global_module, device='cuda:0', max_batch=None, cuda_graph=False):
         super().__init__()
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         self.device = torch.device(device)
         self.local_module, self.global_module = local_module, global_module
         self.densify = getattr(args, 'densify', None)
@@ -26,7 +29,36 @@ class DepthEstimatorFused(nn.Module):
     @torch.no_grad()
     def forward(self, img_ny, gt_depth=None):
         """img_ny [B,2,H,W,3] (dataset-native, already divided by alpha) -> dict(image, sharp, refoc, bndry, depth, conf,
-        depth_map [B,H,W] thresholded as blurry_edges_test.py:144, metrics [B,5] if gt_depth [B,H,W] is given)."""
+        depth_map [B,H,W] thresholded as blurry_edges_test.py:144, metrics [B,5] if gt_depth [B,H,W] is given).
+        With cuda_graph=True the returned tensors are the graph's static outputs: they are overwritten by the next call."""
+        if not self.cuda_graph:
+            return self._run(img_ny, gt_depth)
+        key = (tuple(img_ny.shape), gt_depth is not None)
+        entry = self._graphs.get(key)
+        if entry is None:
+            s_img = torch.empty(tuple(img_ny.shape), device=self.device, dtype=torch.float32)
+            s_gt = None if gt_depth is None else torch.empty(tuple(gt_depth.shape), device=self.device, dtype=torch.float32)
+            s_img.copy_(img_ny)
+            if s_gt is not None:
+                s_gt.copy_(gt_depth)
+            cur, side = torch.cuda.current_stream(self.device), torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # warm-up outside the capture: workspace allocation, cuDNN plans, kernel attributes
+                for _ in range(2):
+                    self._run(s_img, s_gt)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._run(s_img, s_gt)
+            entry = self._graphs[key] = (graph, s_img, s_gt, out)
+        graph, s_img, s_gt, out = entry
+        s_img.copy_(img_ny, non_blocking=True)
+        if s_gt is not None:
+            s_gt.copy_(gt_depth, non_blocking=True)
+        graph.replay()
+        return out
+
+    def _run(self, img_ny, gt_depth=None):
         B, H, W, R, L = img_ny.shape[0], self.H, self.W, self.R, self.L
         if B > self.ctx.max_batch:
             self.ctx.close()

@@ -90,3 +90,35 @@ def test_patch_gather_equals_unfold_permute():
     ctx.call('be_patch_gather', img, 2, vec)
     ref = torch.nn.Unfold(21, stride=2)(img).view(2, 3, 21, 21, g.Hp, g.Wp).permute(0, 4, 5, 1, 2, 3).reshape(2 * g.L, 3, 21, 21)
     assert torch.equal(vec, ref)
+
+
+def test_driver_body_as_cuda_graph_equals_eager():
+    """cuda_graph=True captures gather -> LocalStage -> pass A -> pm -> GlobalStage -> pass B -> metrics once and replays it."""
+    import time
+    from blurry_edges_b200 import DepthEstimatorFused, _lib
+    S, B = GEOMS['mid'], 1
+    args = argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[S, S], batch_size=B, mag=4.0, rho_prime=10.39,
+                              densify=None, crop=10, cam_params=CAMP)
+    local_m, global_m = TinyLocal().cuda(), TinyGlobal().cuda()
+    eager = DepthEstimatorFused(args, local_m, global_m, 'cuda:0')
+    graphed = DepthEstimatorFused(args, local_m, global_m, 'cuda:0', cuda_graph=True)
+    for seed in (101, 102, 103):                       # first call captures, the others replay with new inputs
+        img = synth.image_pairs(B, S, S, seed=seed).cuda()
+        gt = synth.uniform((B, S, S), seed + 10, 0.75, 1.18).cuda()
+        a = eager(img, gt)
+        n0 = _lib.launch_count()
+        b = graphed(img, gt)
+        torch.cuda.synchronize()
+        if seed != 101:
+            assert _lib.launch_count() == n0           # a replay issues no launches from the host
+        for k in a:
+            assert relmax(b[k].cpu().numpy(), a[k].cpu().numpy()) < (2e-6 if k != 'metrics' else 1e-6), k
+    def lat(m):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(20):
+            m(img, gt)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 20
+    te, tg = lat(eager), lat(graphed)
+    print(f'driver body, 1 pair {S}x{S}, stand-in networks: eager {te * 1e6:.0f} us, CUDA graph {tg * 1e6:.0f} us')
+    assert tg < te

@@ -202,3 +202,40 @@ def test_training_repeatability_full_size_stress():
         l1, g1, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
         assert abs(l1 - l0) <= 1e-6 * abs(l0)
         assert float(np.abs(g1 - g0).max()) <= 2e-6 * float(np.abs(g0).max())
+
+
+def test_global_loss_step_is_cuda_graph_capturable():
+    """Both loss stages are stream-ordered with no host synchronisation (the batch mask count stays on the device), so a training
+    step can be captured into a CUDA graph together with the networks around it; replays match the eager step."""
+    from blurry_edges_b200 import GlobalLossFused
+    S, B = GEOMS['mid'], 2
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('mid', 'normal', F32)
+    crit = GlobalLossFused(_gargs(S, B), None, 'cuda:0')
+    crit.update_gamma()
+    dev = [t.cuda() for t in (img_ny, img_gt, bd, deri, zgt)]
+    l_ref, g_ref, _ = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    est = raw.clone().cuda().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            est.grad = None
+            crit(est, *dev).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    est.grad = None
+    with torch.cuda.graph(graph):
+        loss = crit(est, *dev)
+        loss.backward()
+    for scale in (1.0, 0.5):
+        with torch.no_grad():
+            est.copy_(raw.cuda() * scale)
+        graph.replay()
+        torch.cuda.synchronize()
+        if scale == 1.0:
+            assert abs(loss.item() - l_ref) <= 1e-6 * abs(l_ref)
+            assert float(np.abs(est.grad.cpu().numpy() - g_ref).max()) <= 2e-6 * float(np.abs(g_ref).max())
+        else:
+            l2, g2, _ = _run_global(crit, raw * scale, img_ny, img_gt, bd, deri, zgt)
+            assert abs(loss.item() - l2) <= 1e-6 * abs(l2)
+            assert float(np.abs(est.grad.cpu().numpy() - g2).max()) <= 2e-6 * float(np.abs(g2).max())
