@@ -182,7 +182,7 @@ def extra_configs(args, rank, world, dev, barrier):
     its 121 blocks sharded over the ranks, configs[4] densify 'w' with 32 pairs per GPU (256 on 8 GPUs)."""
     import argparse as ap
     import synth
-    from blurry_edges_b200 import BigImageFused, GlobalLossFused, PostProcessFused, shard_blocks
+    from blurry_edges_b200 import BigImageFused, Context, GlobalLossFused, PostProcessFused, _lib, make_config, shard_blocks
     import torch.distributed as dist
     cam = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
     base = dict(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=cam)
@@ -242,6 +242,16 @@ def extra_configs(args, rank, world, dev, barrier):
                     'fwd_bwd_ms': ms_fb, 'bwd_gbs': 3 * nb / ((ms_fb - ms_f) / 1e3) / 1e9,
                     'note': 'working set 1.85 GB >> L2; bwd figure = 3 arrays / (fwd+bwd - fwd) time, includes autograd glue'}
     del xs, gs, xg
+    # ---- pass A (blurry_edges_test.py:125-128, colors_only=True): ridge colours of 2 x 64 single images, reported separately (8d) ----
+    Ba = 64
+    ctx_a = Context(make_config(H=S, W=S, max_batch=Ba), dev)
+    p10 = restore_params(synth.raw_global(2 * Ba, L, seed=340 + rank))[..., :10].contiguous().to(dev)
+    img_a = synth.image_pairs(Ba, S, S, seed=341 + rank).permute(0, 1, 4, 2, 3).reshape(2 * Ba, 3, S, S).contiguous().to(dev)
+    lay_a = _lib.single_planar_layout(S, S)
+    ms = _timed(lambda: ctx_a.colors(p10, img_a, lay_a, _lib.PARAMS_LOCAL10), steps, 3, dev, barrier, world)
+    out['pass_a'] = {'metric': 'patches/sec pass A (ridge colours per single image), 128 images per GPU', 'value': 2 * Ba * L * world / (ms / 1e3),
+                     'unit': 'single-image patches/s', 'ms_per_step': ms}
+    del ctx_a, p10, img_a
     # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
