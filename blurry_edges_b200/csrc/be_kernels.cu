@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(128) be_setup_kernel(const float* __restrict__
     rec[3] = make_float4(P.flip[0], P.flip[1], P.z[0], P.z[1]);
     rec[4] = make_float4(P.inv_eta[0], P.inv_eta[1], P.inv_eta[2], P.inv_eta[3]);
     rec[5] = make_float4(P.eta[0], P.eta[1], P.eta[2], P.eta[3]);
-    rec[6] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // 1 / (sqrt2 * refocus sigma) of the two wedge depths (utils/depth_etas.py:36-37, blurry_edges_test.py:66-74): per-patch
+    // constants, kept off the solver warp's critical path
+    rec[6] = make_float4(1.0f / (BE_SQRT2_F * be_refocus_sigma(cam, P.z[0])), 1.0f / (BE_SQRT2_F * be_refocus_sigma(cam, P.z[1])), 0.f, 0.f);
     rec[7] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gtable) {   // chain-rule scalars of the backward pass
         BePatchGrad G;

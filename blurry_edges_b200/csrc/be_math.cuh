@@ -257,7 +257,16 @@ BE_HD void be_solve_colors(const float* S, float lam, double* Minv, float* C) {
     const double d = (double)S[3] + (double)lam, e = S[4], f = (double)S[5] + (double)lam;
     const double A00 = d * f - e * e, A01 = c * e - b * f, A02 = b * e - c * d;
     const double A11 = a * f - c * c, A12 = b * c - a * e, A22 = a * d - b * b;
-    const double idet = 1.0 / (a * A00 + b * A01 + c * A02);
+    const double det = a * A00 + b * A01 + c * A02;     // >= lam^3 > 0
+#if defined(__CUDA_ARCH__)
+    // 1/det: MUFU.RCP seed + two Newton steps in fp64 (2^-23 -> 2^-46 -> 2^-92) instead of the ~30-instruction IEEE division;
+    // this chain is on the solver warp's critical path, which gates the render warps
+    double idet = (double)be_rcp((float)det);
+    idet = idet * (2.0 - det * idet);
+    idet = idet * (2.0 - det * idet);
+#else
+    const double idet = 1.0 / det;
+#endif
     Minv[0] = A00 * idet; Minv[1] = A01 * idet; Minv[2] = A02 * idet;
     Minv[3] = A11 * idet; Minv[4] = A12 * idet; Minv[5] = A22 * idet;
 #pragma unroll

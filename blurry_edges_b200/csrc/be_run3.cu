@@ -176,9 +176,10 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                         const float* rec = s_rec + (k & 3) * BE_REC;
                         const float z0 = rec[14], z1 = rec[15];
                         const int cnt = (int)S[15];
-                        const float sg1 = (cnt & 1023) > 0 ? be_refocus_sigma(a.cam, z0) : BE_ETA_SHARP;   // blurry_edges_test.py:66-72
-                        const float sg2 = (cnt >> 10) > 0 ? be_refocus_sigma(a.cam, z1) : BE_ETA_SHARP;
-                        col[3] = make_float4(1.0f / (BE_SQRT2_F * sg1), 1.0f / (BE_SQRT2_F * sg2), z0, z1);
+                        const float inv_sharp = 1.0f / (BE_SQRT2_F * BE_ETA_SHARP);
+                        // refocus sigma of a wedge that owns no mask pixel in the patch falls back to 1e-4 (blurry_edges_test.py:66-72);
+                        // rec[24], rec[25] = 1 / (sqrt2 sigma(z)) from be_setup_kernel
+                        col[3] = make_float4((cnt & 1023) > 0 ? rec[24] : inv_sharp, (cnt >> 10) > 0 ? rec[25] : inv_sharp, z0, z1);
                     }
                 } else {
                     // colours [NB][3(channel)][3(wedge)][Hp][Wp]  (blurry_edges_test.py:27 permute)
