@@ -58,16 +58,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed region of
+    the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mx, self.reasons, self.proc, self.stop = index, [], [], set(), None, False
+        self.rows = []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {'hw_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                'hw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                'sw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                'sw_power_cap': getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        try:
+            self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while True:                               # at least one sample, the last one taken after `stop` was requested
+            last = self.stop
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            if last:
+                break
+            time.sleep(0.002)
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20',
                                           '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -80,6 +123,9 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(',')])
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.nvml is not None:
+            self.thread.join(timeout=2)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -89,12 +135,16 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        if self.nvml is not None:
+            sm = sorted(self.sm)
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 2 ms period'}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith('active') for r in self.rows)]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+                'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 def restore_params(raw):
