@@ -45,7 +45,7 @@ API_BYTES_PER_PATCH = 48.0 + 2 * 3 * R * R * 4 + 15 * S * S * 4 / L
 TRAFFIC_NCU_64 = 155.291904e6 + 38.151424e6
 TRAFFIC_NCU = None
 # warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1f_run3_kernel_full.txt)
-WARP_INST_PER_PATCH = 4726.0
+WARP_INST_PER_PATCH = 4613.0
 SM_COUNT, SMSP_PER_SM = 148, 4
 
 
@@ -271,7 +271,12 @@ def extra_configs(args, rank, world, dev, barrier):
 
     ms = _timed(train_step2, steps, 3, dev, barrier, world)
     out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
-                             'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2}
+                             'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2,
+                             'kernels_ncu': {'be_loss2_kernel': {'share_of_step': 0.79, 'warp_inst_per_patch': 12320, 'issue_active': 0.50},
+                                             'be_run3_kernel<TRAINFWD>': {'share_of_step': 0.18},
+                                             'source': 'profiles/r1b_train_launches.txt, profiles/r1c_loss2_kernel_full.txt'},
+                             'algorithmic_bytes_per_patch': 810.0,
+                             'hbm_frac_at_algorithmic_bytes': 810.0 * Bt2 * L / (ms / 1e3) / 1e9 / peaks()[0]}
     del crit2, raw2, img2, gt2, bd2, deri2, zg2
     # ---- the Smish activation of LocalStage, an HBM-bound elementwise kernel (8 B/element fwd, 12 B/element bwd) ----
     from blurry_edges_b200 import smish
