@@ -153,7 +153,7 @@ int pick_runs(const BeGeom& g, int items, int ctas_per_sm, double ovh, int* G, i
     *runs = (g.Wp + bestG - 1) / bestG;
     return 0;
 }
-constexpr int RUN_CTAS = 3, LOSS_CTAS = 2;        // resident CTAs per SM of be_run3_kernel / be_loss2_kernel
+constexpr int RUN_CTAS = 2, COLORS_CTAS = 3, LOSS_CTAS = 2;        // resident CTAs per SM of be_run3_kernel / be_loss2_kernel
 constexpr double RUN_OVH = 5.0, LOSS_OVH = 1.0;   // calibrated: G=64 vs G=32 at 64 pairs differ by 1.9 % (be_run3)
 
 }  // namespace
@@ -279,7 +279,7 @@ int be_colors_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, const flo
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors;
     a.g = c->g; a.cam = c->cam; a.NB = M; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, M, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+    pick_runs(c->g, M, COLORS_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -481,7 +481,7 @@ int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, co
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.img = make_img(dev_img, layout); a.colors = dev_colors; a.blocks = c->blk_dev;
     a.g = c->g; a.cam = c->cam; a.NB = nitem; a.accH = c->g.H; a.accW = c->g.W;
-    pick_runs(c->g, nitem, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+    pick_runs(c->g, nitem, COLORS_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_COLORS, a, st);
     BE_CUDA(cudaGetLastError());
     return 0;

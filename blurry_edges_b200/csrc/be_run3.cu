@@ -83,11 +83,10 @@ template <int MODE>
 struct Smem {
     static constexpr bool INFER = (MODE == BE_RUN_INFER), TRAIN = (MODE == BE_RUN_TRAINFWD);
     static constexpr int NPIX4 = TRAIN ? 4 : 3;                  // (p0,p1) (p2,p3) (p4,p5) [(zgt,-)]  each value a (slot0,slot1) pair
-    static constexpr int NACC4 = INFER ? 8 : (TRAIN ? 4 : 0);    // accumulator pairs 2q, 2q+1
+    static constexpr int NACC = INFER ? 16 : (TRAIN ? 8 : 0);    // accumulators per slot (15 / 7 used), kept in REGISTERS as (slot0, slot1) pairs
     static constexpr int NST4 = INFER ? 4 : (TRAIN ? 3 : 0);     // (d1,d2) (u1a,u2a) (u1b,u2b) [(m1,m2)]
     static constexpr size_t off_pix = 0;
-    static constexpr size_t off_acc = off_pix + sizeof(float4) * NPIX4 * NCOMP;
-    static constexpr size_t off_st = off_acc + sizeof(float4) * NACC4 * NCOMP;
+    static constexpr size_t off_st = off_pix + sizeof(float4) * NPIX4 * NCOMP;
     static constexpr size_t off_rec = off_st + sizeof(float4) * 2 * NST4 * NCOMP;   // float rec[4][BE_REC]
     static constexpr size_t off_part = off_rec + sizeof(float) * 4 * BE_REC;        // float part[2][BE_WARPS][16]
     static constexpr size_t off_col = off_part + sizeof(float) * 2 * BE_WARPS * 16; // float col[2][16]: C0|-, D1|-, D2|-, ir1, ir2, z0, z1
@@ -97,7 +96,7 @@ struct Smem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
+__global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3_kernel(const BeRunArgs a) {
     using SM = Smem<MODE>;
     constexpr bool INFER = SM::INFER, TRAIN = SM::TRAIN, FOLD = INFER || TRAIN;
     constexpr int NIMG = FOLD ? 2 : 1;
@@ -105,7 +104,6 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_pix = reinterpret_cast<float4*>(smem_raw + SM::off_pix);
-    float4* s_acc = reinterpret_cast<float4*>(smem_raw + SM::off_acc);
     float4* s_st = reinterpret_cast<float4*>(smem_raw + SM::off_st);
     float* s_rec = reinterpret_cast<float*>(smem_raw + SM::off_rec);
     float* s_part = reinterpret_cast<float*>(smem_raw + SM::off_part);
@@ -234,8 +232,9 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
     };
 #pragma unroll
     for (int q = 0; q < SM::NPIX4; ++q) s_pix[q * NCOMP + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    f2 acc[SM::NACC > 0 ? SM::NACC : 1];             // overlap sums of the two pixels this thread currently owns
 #pragma unroll
-    for (int q = 0; q < SM::NACC4; ++q) s_acc[q * NCOMP + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < SM::NACC; ++q) acc[q] = bc2(0.0f);
 #pragma unroll
     for (int s = 0; s < 2; ++s)
         if (valid[s]) load_pixel(s, 0);
@@ -331,28 +330,18 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
             const float4* st = s_st + (par * SM::NST4) * NCOMP + tid;
             const f2x2 sd = lds2(st), sa = lds2(st + NCOMP), sb = lds2(st + 2 * NCOMP);
             const f2 d1 = sd.a, d2 = sd.b;
-            float4* acc = s_acc + tid;
             const f2 lb = be_boundary2(d1, d2);                                              // blurry_edges_test.py:59-61
             {   // the two image renders -> accumulators 0..5
-                const f2 P1r = fma2(sa.a, bc2(D1.x), fma2(sa.b, bc2(D2.x), bc2(C0.x)));
-                const f2 P1g = fma2(sa.a, bc2(D1.y), fma2(sa.b, bc2(D2.y), bc2(C0.y)));
-                const f2 P1b = fma2(sa.a, bc2(D1.z), fma2(sa.b, bc2(D2.z), bc2(C0.z)));
-                const f2 P2r = fma2(sb.a, bc2(D1.x), fma2(sb.b, bc2(D2.x), bc2(C0.x)));
-                const f2 P2g = fma2(sb.a, bc2(D1.y), fma2(sb.b, bc2(D2.y), bc2(C0.y)));
-                const f2 P2b = fma2(sb.a, bc2(D1.z), fma2(sb.b, bc2(D2.z), bc2(C0.z)));
-                f2x2 q0 = lds2(acc), q1 = lds2(acc + NCOMP), q2 = lds2(acc + 2 * NCOMP);
-                sts2(acc, add2(q0.a, P1r), add2(q0.b, P1g));
-                sts2(acc + NCOMP, add2(q1.a, P1b), add2(q1.b, P2r));
-                if (TRAIN) {
-                    f2x2 q3 = lds2(acc + 3 * NCOMP);
-                    sts2(acc + 2 * NCOMP, add2(q2.a, P2g), add2(q2.b, P2b));
-                    sts2(acc + 3 * NCOMP, add2(q3.a, lb), q3.b);
-                }
-                if (INFER) sts2(acc + 2 * NCOMP, add2(q2.a, P2g), add2(q2.b, P2b));
+                acc[0] = add2(acc[0], fma2(sa.a, bc2(D1.x), fma2(sa.b, bc2(D2.x), bc2(C0.x))));
+                acc[1] = add2(acc[1], fma2(sa.a, bc2(D1.y), fma2(sa.b, bc2(D2.y), bc2(C0.y))));
+                acc[2] = add2(acc[2], fma2(sa.a, bc2(D1.z), fma2(sa.b, bc2(D2.z), bc2(C0.z))));
+                acc[3] = add2(acc[3], fma2(sb.a, bc2(D1.x), fma2(sb.b, bc2(D2.x), bc2(C0.x))));
+                acc[4] = add2(acc[4], fma2(sb.a, bc2(D1.y), fma2(sb.b, bc2(D2.y), bc2(C0.y))));
+                acc[5] = add2(acc[5], fma2(sb.a, bc2(D1.z), fma2(sb.b, bc2(D2.z), bc2(C0.z))));
+                if (TRAIN) acc[6] = add2(acc[6], lb);
             }
             if (INFER) {
                 const float4 cz = col[3];
-                f2 Qs[3], Qr[3];
                 {   // eta = 1e-4 render (:63-64): |d| >= 4*sqrt2*1e-4 saturates erf to +-1 exactly in fp32, which is the
                     // case for every pixel of most warps -> warp-uniform fast path with identical results
                     const float lim = 4.0f * BE_SQRT2_F * BE_ETA_SHARP;
@@ -364,25 +353,21 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                         h2 = mk2((lo(d2) > 0.0f) ? 1.0f : 0.0f, (hi(d2) > 0.0f) ? 1.0f : 0.0f);
                     }
                     const f2 v1 = mul2(h1, sub2(bc2(1.0f), h2));
-                    Qs[0] = fma2(v1, bc2(D1.x), fma2(h2, bc2(D2.x), bc2(C0.x)));
-                    Qs[1] = fma2(v1, bc2(D1.y), fma2(h2, bc2(D2.y), bc2(C0.y)));
-                    Qs[2] = fma2(v1, bc2(D1.z), fma2(h2, bc2(D2.z), bc2(C0.z)));
+                    acc[6] = add2(acc[6], fma2(v1, bc2(D1.x), fma2(h2, bc2(D2.x), bc2(C0.x))));
+                    acc[7] = add2(acc[7], fma2(v1, bc2(D1.y), fma2(h2, bc2(D2.y), bc2(C0.y))));
+                    acc[8] = add2(acc[8], fma2(v1, bc2(D1.z), fma2(h2, bc2(D2.z), bc2(C0.z))));
                 }
                 {   // refocused render (:73-74)
                     const f2 h1 = be_h2(d1, cz.x), h2 = be_h2(d2, cz.y);
                     const f2 v1 = mul2(h1, sub2(bc2(1.0f), h2));
-                    Qr[0] = fma2(v1, bc2(D1.x), fma2(h2, bc2(D2.x), bc2(C0.x)));
-                    Qr[1] = fma2(v1, bc2(D1.y), fma2(h2, bc2(D2.y), bc2(C0.y)));
-                    Qr[2] = fma2(v1, bc2(D1.z), fma2(h2, bc2(D2.z), bc2(C0.z)));
+                    acc[9] = add2(acc[9], fma2(v1, bc2(D1.x), fma2(h2, bc2(D2.x), bc2(C0.x))));
+                    acc[10] = add2(acc[10], fma2(v1, bc2(D1.y), fma2(h2, bc2(D2.y), bc2(C0.y))));
+                    acc[11] = add2(acc[11], fma2(v1, bc2(D1.z), fma2(h2, bc2(D2.z), bc2(C0.z))));
                 }
                 const f2x2 sm = lds2(st + 3 * NCOMP);                                        // mask weights (:47-57), from phase 1
-                f2x2 q3 = lds2(acc + 3 * NCOMP), q4 = lds2(acc + 4 * NCOMP), q5 = lds2(acc + 5 * NCOMP);
-                f2x2 q6 = lds2(acc + 6 * NCOMP), q7 = lds2(acc + 7 * NCOMP);
-                sts2(acc + 3 * NCOMP, add2(q3.a, Qs[0]), add2(q3.b, Qs[1]));                 // 6, 7
-                sts2(acc + 4 * NCOMP, add2(q4.a, Qs[2]), add2(q4.b, Qr[0]));                 // 8, 9
-                sts2(acc + 5 * NCOMP, add2(q5.a, Qr[1]), add2(q5.b, Qr[2]));                 // 10, 11
-                sts2(acc + 6 * NCOMP, add2(q6.a, lb), fma2(sm.a, bc2(cz.z), fma2(sm.b, bc2(cz.w), q6.b)));   // 12 boundary, 13 depth sum
-                sts2(acc + 7 * NCOMP, add2(q7.a, add2(sm.a, sm.b)), q7.b);                   // 14 depth count
+                acc[12] = add2(acc[12], lb);                                                 // boundary
+                acc[13] = fma2(sm.a, bc2(cz.z), fma2(sm.b, bc2(cz.w), acc[13]));             // depth sum
+                acc[14] = add2(acc[14], add2(sm.a, sm.b));                                   // depth count
             }
 
             // advance the phase-2 cursor; flush the overlap sums of pixels that leave the window (slow path)
@@ -403,10 +388,11 @@ __global__ void __launch_bounds__(NTHR, 3) be_run3_kernel(const BeRunArgs a) {
                     float* dst = a.acc + (((size_t)ib * a.accH + oy + y0 + si[s]) * a.accW + ox + (px0 + kp) * g.stride + jc[s]) * ACCW;
 #pragma unroll
                     for (int q = 0; q < ACCW / 4; ++q) {
-                        float4 v0 = acc[(2 * q) * NCOMP], v1 = acc[(2 * q + 1) * NCOMP];
-                        atomicAdd(reinterpret_cast<float4*>(dst) + q, s ? make_float4(v0.y, v0.w, v1.y, v1.w) : make_float4(v0.x, v0.z, v1.x, v1.z));
-                        if (s) { v0.y = v0.w = v1.y = v1.w = 0.0f; } else { v0.x = v0.z = v1.x = v1.z = 0.0f; }
-                        acc[(2 * q) * NCOMP] = v0; acc[(2 * q + 1) * NCOMP] = v1;
+                        const float4 v = s ? make_float4(hi(acc[4 * q]), hi(acc[4 * q + 1]), hi(acc[4 * q + 2]), hi(acc[4 * q + 3]))
+                                           : make_float4(lo(acc[4 * q]), lo(acc[4 * q + 1]), lo(acc[4 * q + 2]), lo(acc[4 * q + 3]));
+                        atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[4 * q + e] = s ? mk2(lo(acc[4 * q + e]), 0.0f) : mk2(0.0f, hi(acc[4 * q + e]));
                     }
                 }
             }
