@@ -1,21 +1,23 @@
-// be_run3_kernel: the renderer + fused fold, third generation (the hot-path kernel; be_run2.cu stays for A/B runs).
+// be_run3_kernel: the renderer + fused fold (the hot-path kernel; its history is in DESIGN.md section 3.1).
 //
-// Decomposition as in be_run2.cu: one CTA walks a run of consecutive patches of a patch row; 7 render warps own the
-// R x R window pixels as slots (row i, column residue x mod R), two slots per thread, so an image pixel stays with the same
-// thread for every patch of the run that covers it and its overlap sums (the nn.Fold of the reference) are flushed with
-// 16-byte vector reductions only when the pixel leaves the window; an 8th warp sums the warps' normal-equation partials,
-// solves the 3x3 ridge system in fp64 and publishes the colours through named barriers (software pipeline of depth 1:
-// render warps run phase 1 of patch k, then phase 2 of patch k-1).
+// One CTA walks a run of consecutive patches of a patch row.  7 render warps own the R x R window pixels as slots
+// (row i, column residue x mod R), two slots per thread, so an image pixel stays with the same thread for every patch of the run
+// that covers it: its values are loaded once (cp.async into a thread-private shared-memory cell) and its overlap sums (the
+// nn.Fold of the reference) accumulate in REGISTERS and are flushed with 16-byte vector reductions only when the pixel leaves
+// the window.  An 8th warp sums the warps' normal-equation partials, solves the 3x3 ridge system in fp64 and publishes the
+// colours (software pipeline of depth 1: render warps run phase 1 of patch k, then phase 2 of patch k-1; render -> solver
+// through a named barrier, solver -> render through an mbarrier so that render warps never wait for each other).
 //
-// What changed (profiles/r1c_run2_kernel_full.txt: 6 406 warp-instructions per patch, 45 % of them FFMA/FMUL/FADD, issue
-// slots the binding resource):
-//   * the two slots of a thread are computed as the two halves of packed fp32x2 registers (be_pack.cuh: FFMA2/FMUL2/FADD2
-//     take one issue slot for two pixels); all thread-private shared-memory state (pixels, stash, accumulators) is laid out
-//     as (slot0, slot1) pairs so that one LDS.128 yields two packed operands and no register shuffling is needed;
-//   * the flush (address arithmetic, gather of the halves, 4 REDG.128 per slot) moved out of the per-patch path into a slow
-//     path that a warp enters only when one of its <= 3 column residues wraps;
-//   * the depth mask is stashed as two float weights (FFMA instead of compare/select chains), the stash holds u1,u2 instead
-//     of h1,h2, the solver publishes C0, C1-C0, C2-C0 as float4s.
+//   * The two slots of a thread are the two halves of packed fp32x2 registers (be_pack.cuh: FFMA2/FMUL2/FADD2 take one issue
+//     slot for two pixels); thread-private shared-memory state (pixel cache, phase-1 -> phase-2 stash) is laid out as
+//     (slot0, slot1) pairs so that one LDS.128 yields two packed operands and no register shuffling is needed.
+//   * The accumulators live in registers, not shared memory: the kernel is not occupancy bound (2 CTAs/SM run as fast as 3) but
+//     was co-limited by the 128 B/clk shared-memory pipe (36 LDS/STS.128 per thread and patch); 117 registers, 2 CTAs/SM.
+//   * The flush (address arithmetic, gather of the halves, 4 REDG.128 per slot) is a slow path that a warp enters only when one
+//     of its <= 3 column residues wraps.
+//   * The depth mask is stashed as two float weights (FFMA instead of compare/select chains), the stash holds u1,u2 instead
+//     of h1,h2, the solver publishes C0, C1-C0, C2-C0 as float4s; its critical path (it gates the render warps) uses a
+//     MUFU-seeded fp64 reciprocal and per-patch constants precomputed by be_setup_kernel.
 #include "be_internal.h"
 #include "be_pack.cuh"
 
