@@ -29,8 +29,9 @@ constexpr int NTHR = NCOMP + 32;             // + solver warp
 
 template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
 template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
-__device__ __forceinline__ void sync_full(int par) { if (par) bar_sync_id<2>(); else bar_sync_id<1>(); }
-__device__ __forceinline__ void arrive_full(int par) { if (par) bar_arrive_id<2>(); else bar_arrive_id<1>(); }
+__device__ __forceinline__ void sync_full(int p) { if (p == 0) bar_sync_id<1>(); else if (p == 1) bar_sync_id<2>(); else bar_sync_id<3>(); }
+__device__ __forceinline__ void arrive_full(int p) { if (p == 0) bar_arrive_id<1>(); else if (p == 1) bar_arrive_id<2>(); else bar_arrive_id<3>(); }
+constexpr int NBUF = 3;                       // hand-off buffers (stash, partial sums, colours, barriers): pipeline depth 2
 
 // DONE[parity] (colours published) is an mbarrier with one arrival (solver lane 0): a render warp waits for the solver only.
 // (A named barrier here made every render warp wait for all the others once per patch: 19 % of all warp time, ncu r1d.)
@@ -47,23 +48,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
         asm volatile("{.reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
     } while (!ok);
-}
-
-__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
-    float a[8], b[4], c[2];
-    bool hi_ = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = (hi_ ? v[i + 8] : v[i]) + __shfl_xor_sync(FULL, hi_ ? v[i] : v[i + 8], 16);
-    hi_ = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = (hi_ ? a[i + 4] : a[i]) + __shfl_xor_sync(FULL, hi_ ? a[i] : a[i + 4], 8);
-    hi_ = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) c[i] = (hi_ ? b[i + 2] : b[i]) + __shfl_xor_sync(FULL, hi_ ? b[i] : b[i + 2], 4);
-    hi_ = lane & 2;
-    float d = (hi_ ? c[1] : c[0]) + __shfl_xor_sync(FULL, hi_ ? c[0] : c[1], 2);
-    d += __shfl_xor_sync(FULL, d, 1);
-    return d;
 }
 
 __device__ __forceinline__ void cp_async4(unsigned dst, const float* src) {
@@ -89,12 +73,12 @@ struct Smem {
     static constexpr int NST4 = INFER ? 4 : (TRAIN ? 3 : 0);     // (d1,d2) (u1a,u2a) (u1b,u2b) [(m1,m2)]
     static constexpr size_t off_pix = 0;
     static constexpr size_t off_st = off_pix + sizeof(float4) * NPIX4 * NCOMP;
-    static constexpr size_t off_rec = off_st + sizeof(float4) * 2 * NST4 * NCOMP;   // float rec[4][BE_REC]
-    static constexpr size_t off_part = off_rec + sizeof(float) * 4 * BE_REC;        // float part[2][BE_WARPS][16]
-    static constexpr size_t off_col = off_part + sizeof(float) * 2 * BE_WARPS * 16; // float col[2][16]: C0|-, D1|-, D2|-, ir1, ir2, z0, z1
-    static constexpr size_t off_axis = off_col + sizeof(float) * 2 * 16;            // float axis[24]
-    static constexpr size_t off_bar = off_axis + sizeof(float) * 24;                // mbarrier done[2]
-    static constexpr size_t bytes = off_bar + sizeof(unsigned long long) * 2;
+    static constexpr size_t off_rec = off_st + sizeof(float4) * NBUF * NST4 * NCOMP;   // float rec[4][BE_REC]
+    static constexpr size_t off_part = off_rec + sizeof(float) * 4 * BE_REC;        // float4 part[NBUF][BE_WARPS][32 lanes][4] (swizzled)
+    static constexpr size_t off_col = off_part + sizeof(float4) * NBUF * BE_WARPS * 32 * 4; // float col[NBUF][16]: C0|-, D1|-, D2|-, ir1, ir2, z0, z1
+    static constexpr size_t off_axis = off_col + sizeof(float) * NBUF * 16;         // float axis[24]
+    static constexpr size_t off_bar = off_axis + sizeof(float) * 24;                // mbarrier done[NBUF]
+    static constexpr size_t bytes = off_bar + sizeof(unsigned long long) * 4;
 };
 
 template <int MODE>
@@ -108,7 +92,7 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
     float4* s_pix = reinterpret_cast<float4*>(smem_raw + SM::off_pix);
     float4* s_st = reinterpret_cast<float4*>(smem_raw + SM::off_st);
     float* s_rec = reinterpret_cast<float*>(smem_raw + SM::off_rec);
-    float* s_part = reinterpret_cast<float*>(smem_raw + SM::off_part);
+    float4* s_part = reinterpret_cast<float4*>(smem_raw + SM::off_part);
     float* s_col = reinterpret_cast<float*>(smem_raw + SM::off_col);
     float* s_axis = reinterpret_cast<float*>(smem_raw + SM::off_axis);
     unsigned long long* s_done = reinterpret_cast<unsigned long long*>(smem_raw + SM::off_bar);
@@ -134,27 +118,46 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
 
     if (tid < R) s_axis[tid] = be_axis(tid, R);
-    if (tid == NTHR - 1) { mbar_init(s_done, 1); mbar_init(s_done + 1, 1); }
-    if (tid < 16 && (tid >> 3) < n)   // records of patches 0 and 1
+    if (tid == NTHR - 1) { mbar_init(s_done, 1); mbar_init(s_done + 1, 1); mbar_init(s_done + 2, 1); }
+    if (tid < 24 && (tid >> 3) < n)   // records of patches 0, 1 and 2
         reinterpret_cast<float4*>(s_rec)[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
     __syncthreads();
 
     if (warp == BE_WARPS) {
         // ======================================= solver warp =======================================
-        for (int k = 0; k < n; ++k) {
-            const int par = k & 1;
+        int par = 0;                                  // hand-off buffer of patch k: k mod NBUF
+        for (int k = 0; k < n; ++k, par = (par + 1 == NBUF) ? 0 : par + 1) {
             float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < 8 && k + 2 < n) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 2) * BE_REC) + lane);
+            if (lane < 8 && k + 3 < n) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 3) * BE_REC) + lane);
             sync_full(par);
-            float t = 0.0f;
-            if (lane < 16) {
-                const float* pp = s_part + (par * BE_WARPS) * 16 + lane;
+            // The render warps leave their per-lane partial sums (16 values per lane) in shared memory; this warp, which has the
+            // time (the pipeline gives it two patch periods), adds the 7 x 32 rows: lane (g, q) = (lane >> 2, lane & 3) sums
+            // float4 column q of the rows l = g (mod 8), three shuffle levels fold the 8 row groups.  A transposing shuffle
+            // reduction in every render warp would cost 15 SHFL + 30 SEL + 15 FADD per warp and patch (12 % of their instructions).
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                const int gq = lane >> 2, qq = lane & 3;
+                const float4* pp = s_part + (size_t)(par * BE_WARPS) * 128;
 #pragma unroll
-                for (int wv = 0; wv < BE_WARPS; ++wv) t += pp[wv * 16];
+                for (int wv = 0; wv < BE_WARPS; ++wv)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int l = gq + 8 * jj;
+                        const float4 v = pp[(wv * 32 + l) * 4 + ((qq + (l >> 1)) & 3)];
+                        t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+                    }
+#pragma unroll
+                for (int m = 4; m <= 16; m <<= 1) {
+                    t4.x += __shfl_xor_sync(FULL, t4.x, m); t4.y += __shfl_xor_sync(FULL, t4.y, m);
+                    t4.z += __shfl_xor_sync(FULL, t4.z, m); t4.w += __shfl_xor_sync(FULL, t4.w, m);
+                }
             }
             float S[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) S[q] = __shfl_sync(FULL, t, q);
+            for (int q = 0; q < 4; ++q) {
+                S[4 * q + 0] = __shfl_sync(FULL, t4.x, q); S[4 * q + 1] = __shfl_sync(FULL, t4.y, q);
+                S[4 * q + 2] = __shfl_sync(FULL, t4.z, q); S[4 * q + 3] = __shfl_sync(FULL, t4.w, q);
+            }
             double Minv[6];
             float C[9];
             be_solve_colors(S, g.lam, Minv, C);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
                         for (int c = 0; c < 3; ++c) dst[(size_t)(c * 3 + wd) * g.Hp * g.Wp] = C[3 * wd + c];
                 }
             }
-            if (lane < 8 && k + 2 < n) reinterpret_cast<float4*>(s_rec + ((k + 2) & 3) * BE_REC)[lane] = nxt;
+            if (lane < 8 && k + 3 < n) reinterpret_cast<float4*>(s_rec + ((k + 3) & 3) * BE_REC)[lane] = nxt;
             __syncwarp();
             if (lane == 0) mbar_arrive(s_done + par);
         }
@@ -242,10 +245,14 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
         if (valid[s]) load_pixel(s, 0);
     const float inv_sharp = 1.0f / (BE_SQRT2_F * BE_ETA_SHARP);
 
-    for (int k = 0; k <= n; ++k) {
+    // Software pipeline of depth 2: iteration k runs phase 1 of patch k and phase 2 of patch k-2, so the solver warp has two patch
+    // periods for the reduction + solve of a patch before a render warp needs its colours.  b1 = k mod NBUF, b2 = (k-2) mod NBUF.
+    int b1 = 0, b2 = NBUF - 2;
+    unsigned ph2 = 1;                                 // mbarrier phase parity of patch k-2, ((k-2) / NBUF) & 1, after the wrap at k = 2
+    for (int k = 0; k <= n + 1; ++k) {
         // ---------------- phase 1 of patch k (both slots packed) ----------------
         if (k < n) {
-            const int par = k & 1;
+            const int par = b1;
             BePatch P;
             {
                 const float4* q4 = reinterpret_cast<const float4*>(s_rec + (k & 3) * BE_REC);
@@ -309,8 +316,12 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
 #pragma unroll
                 for (int q = 0; q < 16; ++q) ssum[q] = 0.0f;
             }
-            const float tot = warp_reduce16(ssum, lane);
-            if (!(lane & 1)) s_part[(par * BE_WARPS + warp) * 16 + (lane >> 1)] = tot;
+            {   // row of this lane, float4 columns rotated by (lane >> 1) so that the 16-byte stores of a quarter warp hit 8 bank groups
+                float4* row = s_part + ((size_t)(par * BE_WARPS + warp) * 32 + lane) * 4;
+                const int rot = lane >> 1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) row[(c + rot) & 3] = make_float4(ssum[4 * c], ssum[4 * c + 1], ssum[4 * c + 2], ssum[4 * c + 3]);
+            }
             arrive_full(par);
 
             // advance the phase-1 cursor: reload the pixel cache of slots whose image pixel changes
@@ -323,10 +334,10 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
             }
         }
 
-        // ---------------- phase 2 of patch k-1 ----------------
-        if (k >= 1) mbar_wait(s_done + ((k - 1) & 1), ((k - 1) >> 1) & 1);   // colours of patch k-1 are published; s_part[par] is free
-        if (FOLD && k >= 1) {
-            const int kp = k - 1, par = kp & 1;
+        // ---------------- phase 2 of patch k-2 ----------------
+        if (k >= 2) mbar_wait(s_done + b2, ph2);          // colours of patch k-2 are published; its partial-sum buffer is free again
+        if (FOLD && k >= 2) {
+            const int kp = k - 2, par = b2;
             const float4* col = reinterpret_cast<const float4*>(s_col + par * 16);
             const float4 C0 = col[0], D1 = col[1], D2 = col[2];
             const float4* st = s_st + (par * SM::NST4) * NCOMP + tid;
@@ -399,6 +410,8 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
                 }
             }
         }
+        b1 = (b1 + 1 == NBUF) ? 0 : b1 + 1;
+        if (b2 + 1 == NBUF) { b2 = 0; ph2 ^= 1u; } else ++b2;
     }
     if (TRAIN) {
         mcount = __reduce_add_sync(FULL, mcount);
