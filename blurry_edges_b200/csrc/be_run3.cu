@@ -4,9 +4,10 @@
 // (row i, column residue x mod R), two slots per thread, so an image pixel stays with the same thread for every patch of the run
 // that covers it: its values are loaded once (cp.async into a thread-private shared-memory cell) and its overlap sums (the
 // nn.Fold of the reference) accumulate in REGISTERS and are flushed with 16-byte vector reductions only when the pixel leaves
-// the window.  An 8th warp sums the warps' normal-equation partials, solves the 3x3 ridge system in fp64 and publishes the
-// colours (software pipeline of depth 1: render warps run phase 1 of patch k, then phase 2 of patch k-1; render -> solver
-// through a named barrier, solver -> render through an mbarrier so that render warps never wait for each other).
+// the window.  An 8th warp (the solver) adds up the lanes' normal-equation partial sums, solves the 3x3 ridge system in fp64 and
+// publishes the colours.  Software pipeline of depth 2 over three hand-off buffers: a render warp runs phase 1 of patch k, then
+// phase 2 of patch k-2; render -> solver through named barriers (bar.arrive), solver -> render through mbarriers, so that render
+// warps never wait for each other and the solver has two patch periods for its latency chain.
 //
 //   * The two slots of a thread are the two halves of packed fp32x2 registers (be_pack.cuh: FFMA2/FMUL2/FADD2 take one issue
 //     slot for two pixels); thread-private shared-memory state (pixel cache, phase-1 -> phase-2 stash) is laid out as
@@ -15,9 +16,11 @@
 //     was co-limited by the 128 B/clk shared-memory pipe (36 LDS/STS.128 per thread and patch); 117 registers, 2 CTAs/SM.
 //   * The flush (address arithmetic, gather of the halves, 4 REDG.128 per slot) is a slow path that a warp enters only when one
 //     of its <= 3 column residues wraps.
+//   * The cross-lane reduction of the 16 sums is done by the solver warp from shared memory (28 LDS.128 + 3 shuffle levels)
+//     instead of a transposing shuffle reduction in each of the 7 render warps (15 SHFL + 30 SEL + 15 FADD each).
 //   * The depth mask is stashed as two float weights (FFMA instead of compare/select chains), the stash holds u1,u2 instead
-//     of h1,h2, the solver publishes C0, C1-C0, C2-C0 as float4s; its critical path (it gates the render warps) uses a
-//     MUFU-seeded fp64 reciprocal and per-patch constants precomputed by be_setup_kernel.
+//     of h1,h2, the solver publishes C0, C1-C0, C2-C0 as float4s; it uses a MUFU-seeded fp64 reciprocal and per-patch
+//     constants precomputed by be_setup_kernel.
 #include "be_internal.h"
 #include "be_pack.cuh"
 
