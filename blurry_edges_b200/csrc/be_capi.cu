@@ -710,11 +710,24 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
     int bounds[BE_HOST_CHUNKS + 1];
     int nchunk = B < want ? B : want;
     if (ramp_on && B >= 16) {
-        static const int wgt[7] = {1, 2, 3, 4, 3, 2, 1};
-        nchunk = 7;
+        static int wgt[BE_HOST_CHUNKS] = {1, 2, 3, 4, 3, 2, 1};
+        static int nw = 7;
+        static const bool parsed = [] {             // BE_HOST_WGT="1,2,3,..." overrides the ramp (tuning aid)
+            const char* e = getenv("BE_HOST_WGT");
+            if (e) {
+                int k = 0;
+                while (*e && k < BE_HOST_CHUNKS) { wgt[k++] = atoi(e); while (*e && *e != ',') ++e; if (*e == ',') ++e; }
+                if (k > 0) nw = k;
+            }
+            return true;
+        }();
+        (void)parsed;
+        int tot_w = 0;
+        for (int i = 0; i < nw; ++i) tot_w += wgt[i];
+        nchunk = nw;
         int acc_w = 0;
         bounds[0] = 0;
-        for (int i = 0; i < 7; ++i) { acc_w += wgt[i]; bounds[i + 1] = (int)((long long)B * acc_w / 16); }
+        for (int i = 0; i < nw; ++i) { acc_w += wgt[i]; bounds[i + 1] = (int)((long long)B * acc_w / tot_w); }
     } else {
         for (int i = 0; i <= nchunk; ++i) bounds[i] = (int)((long long)B * i / nchunk);
     }
