@@ -21,6 +21,10 @@ GEOS = {
     'R7_s2': dict(R=7, stride=2, H=15, W=15, w=1.0),
     'R21_s5_w05': dict(R=21, stride=5, H=41, W=46, w=0.5),
     'R15_s4_w2': dict(R=15, stride=4, H=31, W=39, w=2.0),
+    # runs of 1, 2 and 3 patches: the prologue / drain of the depth-2 pipeline and its three hand-off buffers
+    'one_patch': dict(R=21, stride=2, H=21, W=21, w=1.0),
+    'two_patches': dict(R=21, stride=2, H=21, W=23, w=1.0),
+    'three_by_three': dict(R=21, stride=2, H=25, W=25, w=1.0),
 }
 
 
