@@ -328,8 +328,10 @@ class Context:
         return terms, loss, grad
 
     # ---- host-buffer entry point (numpy / pinned host tensors in, numpy out) ------------
-    def host_render_fold(self, est, img, layout: BeImageLayout, densify_w=False, param_mode=PARAMS_RESTORED12, out=None):
-        """est, img: CPU float32 contiguous torch tensors (ideally pinned).  Returns 7 CPU tensors."""
+    def host_render_fold(self, est, img, layout: BeImageLayout, densify_w=False, param_mode=PARAMS_RESTORED12, out=None,
+                         want_thresholded=True):
+        """est, img: CPU float32 contiguous torch tensors (ideally pinned).  Returns the six maps of PostProcess.forward
+        (blurry_edges_test.py:100) as CPU tensors, plus the thresholded depth of :144 if want_thresholded."""
         B, H, W = est.shape[0], self.cfg.H, self.cfg.W
         for t in (est, img):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
@@ -337,10 +339,11 @@ class Context:
         if out is None:
             pin = dict(dtype=torch.float32, pin_memory=True)
             out = [torch.empty(B, 2, 3, H, W, **pin), torch.empty(B, 3, H, W, **pin), torch.empty(B, 3, H, W, **pin),
-                   torch.empty(B, 1, H, W, **pin), torch.empty(B, H, W, **pin), torch.empty(B, H, W, **pin),
-                   torch.empty(B, H, W, **pin)]
+                   torch.empty(B, 1, H, W, **pin), torch.empty(B, H, W, **pin), torch.empty(B, H, W, **pin)]
+            if want_thresholded:
+                out.append(torch.empty(B, H, W, **pin))
+        ptrs = [C.c_void_p(t.data_ptr()) for t in out] + ([None] if len(out) == 6 else [])
         with torch.cuda.device(self.device):
             check(self.lib.be_host_render_fold(self.h, C.c_void_p(est.data_ptr()), param_mode, C.c_void_p(img.data_ptr()),
-                                               C.byref(layout), B, int(densify_w),
-                                               *[C.c_void_p(t.data_ptr()) for t in out]))
+                                               C.byref(layout), B, int(densify_w), *ptrs))
         return out

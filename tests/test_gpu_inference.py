@@ -141,7 +141,9 @@ def test_host_buffer_entry_point_equals_device_entry_point():
     host = ctx.host_render_fold(est.pin_memory(), img.pin_memory(), _lib.planar_layout(S, S))
     for d, h in zip(dev, host):
         assert relmax(h.numpy(), d.numpy()) < 2e-6
-    # pageable output arrays take the cudaMemcpyAsync route instead of the export kernel: same bits
+    six = ctx.host_render_fold(est.pin_memory(), img.pin_memory(), _lib.planar_layout(S, S), want_thresholded=False)
+    assert len(six) == 6 and all(relmax(a.numpy(), b.numpy()) < 2e-6 for a, b in zip(six, host))
+    # pageable output arrays (synchronous staging inside cudaMemcpyAsync) give the same result
     pageable = [torch.full_like(h, float('nan')).clone() for h in host]
     assert not any(t.is_pinned() for t in pageable)
     ctx.host_render_fold(est, img, _lib.planar_layout(S, S), out=pageable)
