@@ -1,25 +1,48 @@
-// be_loss2_kernel: global-stage loss forward + analytic backward (global_training.py:62-157), second generation.
+// be_loss2_kernel: global-stage loss forward + analytic backward (global_training.py:62-157).
 //
-// Same mathematics as be_loss_kernel<false> of be_train.cu (which stays as the local-stage kernel), restructured after its
-// ncu capture (profiles/r1_loss_kernel_full.txt: 19 225 warp-instructions per patch, issue slots 49 % busy, 7 CTA barriers
-// and two serial fp64 solves per patch, 2 CTAs/SM):
+// Same mathematics as the local-stage kernel of be_train.cu, restructured after the ncu captures of its predecessors
+// (profiles/r1_loss_kernel_full.txt: 19 225 warp-instructions per patch, 7 CTA barriers and two serial fp64 solves per patch;
+// profiles/r1j_train_kernels_full.txt: 11 293, three CTA barriers, every warp repeating the second solve):
 //   * the ridge colours C and the inverse normal matrix M^-1 of every patch come from the TRAINFWD render pass that has to run
-//     first anyway (its solver warp stores a 64-byte record per patch), so the loss kernel has no phase-1 sums, no first
-//     reduction, no fp64 solve and two barriers less;
-//   * the second solve V = M^-1 A^T G, S = V C^T + C V^T is done redundantly by every warp in fp32 (80 instructions) instead of
-//     by warp 0 between two CTA barriers; the chain rule to the raw parameters of patch k-1 is done by one (rotating) warp
-//     while the others already work on patch k: 3 CTA barriers per patch instead of 7, no serial section;
-//   * the two pixel slots of a thread are the two halves of packed fp32x2 registers (be_pack.cuh) wherever the operands do
-//     not come straight from a vector load.
+//     first anyway (its solver warp stores a 64-byte record per patch): no phase-1 sums, no first reduction, no fp64 solve here;
+//   * 7 render warps (two packed pixel slots per thread, be_pack.cuh) + one HELPER warp.  Everything that crosses lanes goes to the
+//     helper through shared memory: it adds up the lanes' A^T G partial sums, does the second solve V = M^-1 A^T G,
+//     S = V C^T + C V^T once (not once per warp), later adds up the 14 backward sums and applies the chain rule to the raw
+//     parameters, and prefetches the next patch's records.  The render warps hand over with bar.arrive (non-blocking) and wait
+//     for V, S on an mbarrier, behind the part of the backward pass that does not depend on them (edge geometry, boundary and
+//     depth terms); the two remaining barriers (the Sobel stencil exchanges) are named barriers of the render warps only;
+//   * the Sobel stages exchange neighbours through shared memory in PAIR layout (see s_X below) so that their FMAs are packed too;
+//     R = 21 is a template constant (neighbour offsets become immediates).
 #include "be_internal.h"
 #include "be_pack.cuh"
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int NT = BE_THREADS;               // 224 threads, 7 warps, two pixel slots per thread
+constexpr int NT = BE_THREADS;               // 224 render threads, 7 warps, two pixel slots per thread
+constexpr int NTHR = NT + 32;                // + helper warp
 constexpr int HALO = BE_MAX_R + 1;
 constexpr int NE = NT + 2 * HALO;
+constexpr size_t DYN_SMEM = sizeof(float4) * (9 * NE + BE_WARPS * 32 * 3 + BE_WARPS * 32 * 4 + 2 * NT);
+
+template <int ID, int COUNT> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+constexpr int BAR_RENDER = 1, BAR_ATG = 2, BAR_SUMS = 3;      // 0 = __syncthreads
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{.reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
 
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
@@ -39,23 +62,27 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
 }
 
 template <int RCT>   // RCT = 21: patch size known at compile time (neighbour offsets become immediates), 0: generic
-// 128 registers (2 CTAs/SM): capped at 80 for 3 CTAs/SM the kernel spills 284 bytes and is 4 % slower (measured)
-__global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
+__global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     __shared__ __align__(16) float s_rec[2][BE_REC];
     __shared__ __align__(16) float s_grec[2][BE_GREC];
     __shared__ __align__(16) float s_crec[2][BE_CREC];
     __shared__ float s_axis[BE_MAX_R + 3];
-    __shared__ float s_part[BE_WARPS][16];
-    __shared__ float s_part3[BE_WARPS][16];
+    __shared__ float s_part[BE_WARPS][16];          // end of kernel: loss partial sums per warp
+    __shared__ __align__(16) float s_VS[16];        // V[9], S[6] of the current patch (helper -> render warps)
+    __shared__ unsigned long long s_vready;         // mbarrier: s_VS published
     // Stencil exchange planes in PAIR layout: entry e holds, per channel, (value at pixel e-HALO, value at pixel e-HALO+NT), so the
     // neighbour of both slots of thread t at offset `off` is the one entry t+HALO+off (3 LDS.128 for 6 channels of two pixels).
     // Pixels within HALO of the seam are written twice (as the low half of their own entry and as the high half of the entry NT
     // below); entries outside the patch stay zero.  Row wrap-around needs no mask: a wrapped neighbour is a border pixel, whose
     // Sobel gradients are zero, and only interior pixels (which never wrap) use the rendered-patch plane.
-    __shared__ float4 s_X[9 * NE];
-    float4* const s_P2 = s_X;                     // [3][NE] rendered patch: (c0,c1) (c2,c3) (c4,c5)
+    extern __shared__ float4 s_dyn[];             // 69 KB: above the 48 KB static limit
+    float4* const s_X = s_dyn;                    // [9][NE]
+    float4* const s_P2 = s_X;                     // [3][NE] (2 used) wedge weights of the rendered patch: (u1, u2) image 1, (u1, u2) image 2
     float4* const s_G2 = s_X + 3 * NE;            // [6][NE] Sobel gradients: gx (c0,c1) (c2,c3) (c4,c5), gy (c0,c1) (c2,c3) (c4,c5)
-    __shared__ float4 s_stash[2][NT];            // thread-private: (d1, d2) and (global boundary, bndry_dist) pairs, stage A -> D
+    float4* const s_partA = s_X + 9 * NE;         // [7*32][3] per-lane A^T G partial sums (9 of 12 floats used), rows of 48 bytes
+    float4* const s_partB = s_partA + BE_WARPS * 32 * 3;   // [7*32][4] per-lane backward sums (14 of 16 used), rows of 64 bytes, swizzled
+    float4* const s_stash0 = s_partB + BE_WARPS * 32 * 4;  // [NT] thread-private (d1, d2) pairs, stage A -> D
+    float4* const s_stash1 = s_stash0 + NT;                // [NT] thread-private (global boundary, bndry_dist) pairs
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const BeGeom g = a.g;
@@ -69,8 +96,9 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
     const int n = min(a.G, g.Wp - px0);
     const int y0 = py * g.stride;
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
+    const int np = 12;
 
-    // records of the first patch: lanes 0-7 table, 8-10 gtable, 11-14 crec
+    // per-patch records: lanes 0-7 table, 8-10 gtable, 11-14 crec
     auto fetch = [&](size_t patch, int l) -> float4 {
         if (l < 8) return __ldg(reinterpret_cast<const float4*>(a.table + patch * BE_REC) + l);
         if (l < 8 + BE_GREC / 4) return __ldg(reinterpret_cast<const float4*>(a.gtable + patch * BE_GREC) + (l - 8));
@@ -84,7 +112,109 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
     constexpr int NFETCH = 8 + BE_GREC / 4 + BE_CREC / 4;
     if (tid < R) s_axis[tid] = be_axis(tid, R);
     if (tid < NFETCH) stash(0, tid, fetch(patch0, tid));
+    if (tid == NTHR - 1) mbar_init(&s_vready, 1);
+    for (int i = tid; i < 9 * NE; i += NTHR) s_X[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
 
+    if (warp == BE_WARPS) {
+        // =========================================== helper warp ===========================================
+        for (int k = 0; k < n; ++k) {
+            const int cur = k & 1;
+            float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < NFETCH && k + 1 < n) nxt = fetch(patch0 + k + 1, lane);
+            bar_sync_id<BAR_ATG, NTHR>();                  // A^T G partial sums of patch k are in s_partA
+            if (lane < NFETCH && k + 1 < n) stash(cur ^ 1, lane, nxt);       // nobody reads the other record buffer any more
+            const int gq = lane >> 2, qq = lane & 3;
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (qq < 3) {
+#pragma unroll
+                for (int wv = 0; wv < BE_WARPS; ++wv)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float4 v = s_partA[(wv * 32 + gq + 8 * jj) * 3 + qq];
+                        t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+                    }
+            }
+#pragma unroll
+            for (int m = 4; m <= 16; m <<= 1) {
+                t4.x += __shfl_xor_sync(FULL, t4.x, m); t4.y += __shfl_xor_sync(FULL, t4.y, m);
+                t4.z += __shfl_xor_sync(FULL, t4.z, m); t4.w += __shfl_xor_sync(FULL, t4.w, m);
+            }
+            float AtG[9];
+            AtG[0] = __shfl_sync(FULL, t4.x, 0); AtG[1] = __shfl_sync(FULL, t4.y, 0); AtG[2] = __shfl_sync(FULL, t4.z, 0);
+            AtG[3] = __shfl_sync(FULL, t4.w, 0); AtG[4] = __shfl_sync(FULL, t4.x, 1); AtG[5] = __shfl_sync(FULL, t4.y, 1);
+            AtG[6] = __shfl_sync(FULL, t4.z, 1); AtG[7] = __shfl_sync(FULL, t4.w, 1); AtG[8] = __shfl_sync(FULL, t4.x, 2);
+            {   // second solve of the ridge backward: V = M^-1 (A^T G), S = V C^T + C V^T (be_backsolve, fp32)
+                float C[9], Mi[6], V[9], Ssym[6];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) C[i] = s_crec[cur][i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Mi[i] = s_crec[cur][9 + i];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
+                    V[0 + c] = Mi[0] * b0 + Mi[1] * b1 + Mi[2] * b2;
+                    V[3 + c] = Mi[1] * b0 + Mi[3] * b1 + Mi[4] * b2;
+                    V[6 + c] = Mi[2] * b0 + Mi[4] * b1 + Mi[5] * b2;
+                }
+                const int pi_[6] = {0, 0, 0, 1, 1, 2}, pj_[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float sacc = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sacc += V[3 * pi_[i] + c] * C[3 * pj_[i] + c] + C[3 * pi_[i] + c] * V[3 * pj_[i] + c];
+                    Ssym[i] = sacc;
+                }
+                if (lane == 0) {
+                    float4* o = reinterpret_cast<float4*>(s_VS);
+                    o[0] = make_float4(V[0], V[1], V[2], V[3]); o[1] = make_float4(V[4], V[5], V[6], V[7]);
+                    o[2] = make_float4(V[8], Ssym[0], Ssym[1], Ssym[2]); o[3] = make_float4(Ssym[3], Ssym[4], Ssym[5], 0.0f);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_vready);
+            bar_sync_id<BAR_SUMS, NTHR>();                 // the 14 backward sums of patch k are in s_partB
+            t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int wv = 0; wv < BE_WARPS; ++wv)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int l = gq + 8 * jj;
+                    const float4 v = s_partB[(wv * 32 + l) * 4 + ((qq + (l >> 1)) & 3)];
+                    t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
+                }
+#pragma unroll
+            for (int m = 4; m <= 16; m <<= 1) {
+                t4.x += __shfl_xor_sync(FULL, t4.x, m); t4.y += __shfl_xor_sync(FULL, t4.y, m);
+                t4.z += __shfl_xor_sync(FULL, t4.z, m); t4.w += __shfl_xor_sync(FULL, t4.w, m);
+            }
+            float S[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                S[4 * q + 0] = __shfl_sync(FULL, t4.x, q); S[4 * q + 1] = __shfl_sync(FULL, t4.y, q);
+                S[4 * q + 2] = __shfl_sync(FULL, t4.z, q); S[4 * q + 3] = __shfl_sync(FULL, t4.w, q);
+            }
+            // chain rule of global_training.py:141-145 backward: 14 per-patch sums -> 12 raw-parameter gradients
+            if (lane == 0 && a.grad != nullptr) {
+                const float* gr = s_grec[cur];      // deta_dcoef[4], dz_deta[4], xy_scale, ang_scale
+                const float xs = gr[8], as = gr[9];
+                float4 o0, o1, o2;
+                o0.x = xs * S[0]; o0.y = xs * S[1]; o0.z = xs * S[4]; o0.w = xs * S[5];
+                o1.x = as * (S[2] + S[3]); o1.y = as * S[3]; o1.z = as * (S[6] + S[7]); o1.w = as * S[7];
+                o2.x = (S[8] + S[12] * gr[4]) * gr[0];
+                o2.y = (S[9] + S[13] * gr[6]) * gr[1];
+                o2.z = (S[10] + S[12] * gr[5]) * gr[2];
+                o2.w = (S[11] + S[13] * gr[7]) * gr[3];
+                float4* o4 = reinterpret_cast<float4*>(a.grad + (patch0 + k) * np);     // 48-byte rows: 16-byte aligned
+                o4[0] = o0; o4[1] = o1; o4[2] = o2;
+            }
+        }
+        __syncthreads();      // matches the render warps' barrier before the loss partial sums
+        __syncthreads();
+        return;
+    }
+
+    // =========================================== render warps ===========================================
     bool valid[2], interior[2];
     int q[2], pi[2], pj[2];
 #pragma unroll
@@ -95,7 +225,6 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
         pi[s] = q[s] / R; pj[s] = q[s] % R;
         interior[s] = valid[s] && pi[s] >= 1 && pi[s] <= R - 2 && pj[s] >= 1 && pj[s] <= R - 2;
     }
-    for (int i = tid; i < 9 * NE; i += NT) s_X[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     // store one pair-layout entry (+ the duplicates near the seam) of `nch` channels given as (slot0, slot1) pairs
     auto store_pairs = [&](float4* plane0, const f2* v, int nch) {
 #pragma unroll
@@ -116,48 +245,18 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
     };
     const f2 mI = mk2(interior[0] ? 1.0f : 0.0f, interior[1] ? 1.0f : 0.0f);
     const f2 kIs = mul2(bc2(2.0f * a.ks), mI), kIsc = mul2(bc2(2.0f * a.ksc), mI);    // Sobel-loss weights, zero off the interior
-    __syncthreads();
     const f2 Y = mk2(s_axis[pi[0]], s_axis[pi[1]]), X = mk2(s_axis[pj[0]], s_axis[pj[1]]);
     const float vm0 = (RCT == BE_MAX_R || valid[0]) ? 1.0f : 0.0f, vm1 = valid[1] ? 1.0f : 0.0f;   // R = 21: every thread has a low pixel
     const float kd = a.gamma_d / (float)(*a.mask_count);
     const size_t TPS = (size_t)a.NB * g.H * g.W * 4;      // floats between consecutive float4 planes of T
-    const int np = 12;
     const float k2c = 2.0f * a.kc, k2cc = 2.0f * a.kcc;
 
     float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     auto fold = [&](f2 v) { return (RCT == BE_MAX_R) ? fmaf(hi(v), vm1, lo(v)) : fmaf(hi(v), vm1, lo(v) * vm0); };       // both slots of a thread, padding slots dropped
 
-    // chain rule of one finished patch (global_training.py:141-145 backward): 14 per-patch sums -> 12 raw-parameter gradients
-    auto chain = [&](int kp) {
-        float t = 0.0f;
-        if (lane < 16) {
-#pragma unroll
-            for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part3[wv][lane];
-        }
-        float S[14];
-#pragma unroll
-        for (int i = 0; i < 14; ++i) S[i] = __shfl_sync(FULL, t, i);
-        if (lane == 0 && a.grad != nullptr) {
-            const float* gr = s_grec[kp & 1];      // deta_dcoef[4], dz_deta[4], xy_scale, ang_scale
-            float* out = a.grad + (patch0 + kp) * np;
-            const float xs = gr[8], as = gr[9];
-            float4 o0, o1, o2;
-            o0.x = xs * S[0]; o0.y = xs * S[1]; o0.z = xs * S[4]; o0.w = xs * S[5];
-            o1.x = as * (S[2] + S[3]); o1.y = as * S[3]; o1.z = as * (S[6] + S[7]); o1.w = as * S[7];
-            o2.x = (S[8] + S[12] * gr[4]) * gr[0];
-            o2.y = (S[9] + S[13] * gr[6]) * gr[1];
-            o2.z = (S[10] + S[12] * gr[5]) * gr[2];
-            o2.w = (S[11] + S[13] * gr[7]) * gr[3];
-            float4* o4 = reinterpret_cast<float4*>(out);     // 48-byte rows: 16-byte aligned
-            o4[0] = o0; o4[1] = o1; o4[2] = o2;
-        }
-    };
-
     for (int k = 0; k < n; ++k) {
         const int cur = k & 1;
         const int x0 = (px0 + k) * g.stride;
-        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (warp == 0 && lane < NFETCH && k + 1 < n) nxt = fetch(patch0 + k + 1, lane);
         auto load_patch = [&](BePatch& P) {
             const float4* q4 = reinterpret_cast<const float4*>(s_rec[cur]);
             const float4 r0 = q4[0], r1 = q4[1], r2 = q4[2], r3 = q4[3], r4 = q4[4];
@@ -195,7 +294,7 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
             }
             f2 d1, d2;
             be_pixel_dists2(P, X, Y, g.w, &d1, &d2);
-            f2 Pv[6];
+            f2 Pv[6], U[4];                           // U = (u1, u2) of image 1, (u1, u2) of image 2
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 h[2 * m] = be_h2(d1, P.inv_eta[2 * m]);
@@ -204,8 +303,11 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
                 const f2 u0 = mul2(sub2(bc2(1.0f), h[2 * m]), gg), u1 = mul2(h[2 * m], gg), u2 = h[2 * m + 1];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) Pv[3 * m + c] = fma2(u0, bc2(C[c]), fma2(u1, bc2(C[3 + c]), mul2(u2, bc2(C[6 + c]))));
+                U[2 * m] = u1; U[2 * m + 1] = u2;
             }
-            store_pairs(s_P2, Pv, 6);
+            // The Sobel filter is linear and P_c = C0_c + u1 (C1_c - C0_c) + u2 (C2_c - C0_c): the stencil stage needs the neighbours'
+            // u1, u2 of the two images (4 values), not their 6 rendered channels - a third less shared-memory traffic in stage B.
+            store_pairs(s_P2, U, 4);
             float gb_[2], bd_[2], Gs[2][6];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
@@ -228,13 +330,10 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
             }
 #pragma unroll
             for (int c = 0; c < 6; ++c) G[c] = mk2(Gs[0][c], Gs[1][c]);
-            s_stash[0][tid] = make_float4(lo(d1), hi(d1), lo(d2), hi(d2));
-            s_stash[1][tid] = make_float4(gb_[0], gb_[1], bd_[0], bd_[1]);
+            s_stash0[tid] = make_float4(lo(d1), hi(d1), lo(d2), hi(d2));
+            s_stash1[tid] = make_float4(gb_[0], gb_[1], bd_[0], bd_[1]);
         }
-        __syncthreads();   // (X1) rendered patch visible
-
-        // chain rule of the previous patch, by one warp, while the others go on
-        if (k >= 1 && warp == (k - 1) % BE_WARPS) chain(k - 1);
+        bar_sync_id<BAR_RENDER, NT>();   // (X1) rendered patch visible to the render warps
 
         // ---------------- stage B: Sobel magnitude of the rendered patch, its loss and gradient (both slots packed) ----------------
         {
@@ -245,9 +344,9 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
                 t7[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
                 t8[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
             }
-            f2 sx[6], sy[6];
+            f2 ux[4], uy[4];                           // Sobel responses of (u1, u2) of image 1 and of image 2
 #pragma unroll
-            for (int c = 0; c < 6; ++c) sx[c] = sy[c] = bc2(0.0f);
+            for (int c = 0; c < 4; ++c) ux[c] = uy[c] = bc2(0.0f);
 #pragma unroll
             for (int oi = -1; oi <= 1; ++oi)
 #pragma unroll
@@ -256,14 +355,28 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
                     const float wx = (float)(((oi == 0) ? 2 : 1) * oj);       // sobel_x[oi+1][oj+1]
                     const float wy = (float)(-oi * ((oj == 0) ? 2 : 1));      // sobel_y[oi+1][oj+1]
                     const float4* pn = s_P2 + (tid + HALO + oi * R + oj);
-                    const float4 v0 = pn[0], v1 = pn[NE], v2 = pn[2 * NE];
-                    const f2 pv[6] = {mk2(v0.x, v0.y), mk2(v0.z, v0.w), mk2(v1.x, v1.y), mk2(v1.z, v1.w), mk2(v2.x, v2.y), mk2(v2.z, v2.w)};
+                    const float4 v0 = pn[0], v1 = pn[NE];
+                    const f2 uv[4] = {mk2(v0.x, v0.y), mk2(v0.z, v0.w), mk2(v1.x, v1.y), mk2(v1.z, v1.w)};
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) {
-                        if (wx != 0.0f) sx[c] = fma2(bc2(wx), pv[c], sx[c]);
-                        if (wy != 0.0f) sy[c] = fma2(bc2(wy), pv[c], sy[c]);
+                    for (int c = 0; c < 4; ++c) {
+                        if (wx != 0.0f) ux[c] = fma2(bc2(wx), uv[c], ux[c]);
+                        if (wy != 0.0f) uy[c] = fma2(bc2(wy), uv[c], uy[c]);
                     }
                 }
+            f2 sx[6], sy[6];
+            {
+                float D1[3], D2[3];
+                const float* cc = s_crec[cur];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { D1[c] = cc[3 + c] - cc[c]; D2[c] = cc[6 + c] - cc[c]; }
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        sx[3 * m + c] = fma2(ux[2 * m], bc2(D1[c]), mul2(ux[2 * m + 1], bc2(D2[c])));
+                        sy[3 * m + c] = fma2(uy[2 * m], bc2(D1[c]), mul2(uy[2 * m + 1], bc2(D2[c])));
+                    }
+            }
             const float dgt[2][6] = {{t6[0].x, t6[0].y, t6[0].z, t6[0].w, t7[0].x, t7[0].y}, {t6[1].x, t6[1].y, t6[1].z, t6[1].w, t7[1].x, t7[1].y}};
             const float dgi[2][6] = {{t7[0].z, t7[0].w, t8[0].x, t8[0].y, t8[0].z, t8[0].w}, {t7[1].z, t7[1].w, t8[1].x, t8[1].y, t8[1].z, t8[1].w}};
             f2 gxy[12], l3 = bc2(0.0f), l4 = bc2(0.0f);
@@ -283,10 +396,9 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
             lossacc[4] = fmaf(lo(l4), lo(mI), fmaf(hi(l4), hi(mI), lossacc[4]));
             store_pairs(s_G2, gxy, 12);
         }
-        __syncthreads();   // (X2) Sobel gradients visible
+        bar_sync_id<BAR_RENDER, NT>();   // (X2) Sobel gradients visible
 
-        // ---------------- stage C: Sobel adjoint into G, then A^T G ----------------
-        if (warp == 0 && lane < NFETCH && k + 1 < n) stash(cur ^ 1, lane, nxt);     // visible after barrier (R2)
+        // ---------------- stage C: Sobel adjoint into G, A^T G partial sums -> helper ----------------
         {
 #pragma unroll
             for (int di = -1; di <= 1; ++di)
@@ -321,15 +433,14 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) sums[3 * wd + c] = fma2(u[wd], G[3 * m + c], sums[3 * wd + c]);
             }
-            float ssum[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ssum[i] = (i < 9) ? fold(sums[i]) : 0.0f;
-            const float tot = warp_reduce16(ssum, lane);
-            if (!(lane & 1)) s_part[warp][lane >> 1] = tot;
+            float4* row = s_partA + (warp * 32 + lane) * 3;
+            row[0] = make_float4(fold(sums[0]), fold(sums[1]), fold(sums[2]), fold(sums[3]));
+            row[1] = make_float4(fold(sums[4]), fold(sums[5]), fold(sums[6]), fold(sums[7]));
+            row[2] = make_float4(fold(sums[8]), 0.0f, 0.0f, 0.0f);
         }
-        __syncthreads();   // (R2) A^T G partials visible
+        bar_arrive_id<BAR_ATG, NTHR>();
 
-        // ---------------- stage D: second solve (every warp), per-pixel backward -> 14 per-patch sums ----------------
+        // ---------------- stage D: per-pixel backward -> 14 per-patch sums -> helper ----------------
         {
             BePatch P;
             float C[9];
@@ -344,41 +455,51 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
                 ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
                 zgv[s] = __ldg(tp[s] + 5 * TPS);
             }
-            const float4 sd = s_stash[0][tid], sg = s_stash[1][tid];
+            const float4 sd = s_stash0[tid], sg = s_stash1[tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);
-            float V[9], Ssym[6];
-            {
-                float t = 0.0f;
-                if (lane < 16) {
-#pragma unroll
-                    for (int wv = 0; wv < BE_WARPS; ++wv) t += s_part[wv][lane];
-                }
-                float AtG[9], Mi[6];
-#pragma unroll
-                for (int i = 0; i < 9; ++i) AtG[i] = __shfl_sync(FULL, t, i);
-#pragma unroll
-                for (int i = 0; i < 6; ++i) Mi[i] = s_crec[cur][9 + i];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
-                    V[0 + c] = Mi[0] * b0 + Mi[1] * b1 + Mi[2] * b2;
-                    V[3 + c] = Mi[1] * b0 + Mi[3] * b1 + Mi[4] * b2;
-                    V[6 + c] = Mi[2] * b0 + Mi[4] * b1 + Mi[5] * b2;
-                }
-                const int pi_[6] = {0, 0, 0, 1, 1, 2}, pj_[6] = {0, 1, 2, 1, 2, 2};
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float sacc = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) sacc += V[3 * pi_[i] + c] * C[3 * pj_[i] + c] + C[3 * pi_[i] + c] * V[3 * pj_[i] + c];
-                    Ssym[i] = sacc;
-                }
-            }
-            const float Sm[9] = {Ssym[0], Ssym[1], Ssym[2], Ssym[1], Ssym[3], Ssym[4], Ssym[2], Ssym[4], Ssym[5]};
+            // -- part 1: everything that does not depend on V, S (runs while the helper reduces and solves) --
             f2 sums[14];
+            f2 coef1[4], coef2[4];                 // d(sums[0..3]) / d gd1 and d(sums[4..7]) / d gd2: the edge geometry of the two wedges
 #pragma unroll
-            for (int i = 0; i < 14; ++i) sums[i] = bc2(0.0f);
-            f2 gd1 = bc2(0.0f), gd2 = bc2(0.0f);
+            for (int i = 0; i < 4; ++i) coef1[i] = coef2[i] = bc2(0.0f);
+            be_wedge_backward2(P, 0, X, Y, g.w, bc2(1.0f), coef1);
+            be_wedge_backward2(P, 1, X, Y, g.w, bc2(1.0f), coef2);
+            const f2 lb = be_boundary2(d1, d2);
+            const f2 bl = mul2(bdv, lb);
+            lossacc[5] += fold(mul2(bl, bl));
+            const f2 eb = sub2(lb, gbv);
+            lossacc[2] += fold(mul2(eb, eb));
+            const f2 glb = fma2(bc2(2.0f * a.kbc), eb, mul2(mul2(bc2(2.0f * a.kbl), bdv), bl));
+            f2 gd1, gd2;
+            {
+                float gb1[2], gb2[2], l6[2], s12[2], s13[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const float d1s = s ? hi(d1) : lo(d1), d2s = s ? hi(d2) : lo(d2);
+                    be_boundary_backward1(d1s, d2s, s ? hi(lb) : lo(lb), s ? hi(glb) : lo(glb), &gb1[s], &gb2[s]);
+                    const int mk = be_mask(d1s, d2s, false);                                       // global_training.py:84-90,121-127
+                    const bool on = (zgv[s] != 0.0f) && (mk != 0);
+                    const float e2 = on ? (((mk == 1) ? P.z[0] : P.z[1]) - zgv[s]) : 0.0f;
+                    l6[s] = e2 * e2;
+                    const float ge = on ? 2.0f * kd * e2 : 0.0f;          // select, not multiply: kd is inf when the batch mask is empty
+                    s12[s] = (mk == 1) ? ge : 0.0f;
+                    s13[s] = (mk == 1) ? 0.0f : ge;
+                }
+                lossacc[6] += fold(mk2(l6[0], l6[1]));
+                sums[12] = mk2(s12[0], s12[1]); sums[13] = mk2(s13[0], s13[1]);
+                gd1 = mk2(gb1[0], gb1[1]); gd2 = mk2(gb2[0], gb2[1]);
+            }
+            // -- part 2: the ridge backward through V, S --
+            mbar_wait(&s_vready, (unsigned)(k & 1));
+            float V[9], Sm[9];
+            {
+                const float4* vs = reinterpret_cast<const float4*>(s_VS);
+                const float4 v0 = vs[0], v1 = vs[1], v2 = vs[2], v3 = vs[3];
+                V[0] = v0.x; V[1] = v0.y; V[2] = v0.z; V[3] = v0.w; V[4] = v1.x; V[5] = v1.y; V[6] = v1.z; V[7] = v1.w; V[8] = v2.x;
+                Sm[0] = v2.y; Sm[1] = v2.z; Sm[2] = v2.w; Sm[3] = v2.z; Sm[4] = v3.x; Sm[5] = v3.y; Sm[6] = v2.w; Sm[7] = v3.y; Sm[8] = v3.z;
+            }
+#pragma unroll
+            for (int i = 8; i < 12; ++i) sums[i] = bc2(0.0f);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 const f2 h1 = h[2 * m], h2 = h[2 * m + 1];
@@ -407,39 +528,20 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
                 be_h_grad2(d2, P.inv_eta[2 * m + 1], &da, &de);
                 gd2 = fma2(gh2, da, gd2); sums[9 + 2 * m] = fma2(gh2, de, sums[9 + 2 * m]);
             }
-            const f2 lb = be_boundary2(d1, d2);
-            const f2 bl = mul2(bdv, lb);
-            lossacc[5] += fold(mul2(bl, bl));
-            const f2 eb = sub2(lb, gbv);
-            lossacc[2] += fold(mul2(eb, eb));
-            const f2 glb = fma2(bc2(2.0f * a.kbc), eb, mul2(mul2(bc2(2.0f * a.kbl), bdv), bl));
-            float gb1[2], gb2[2], l6[2], s12[2], s13[2];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const float d1s = s ? hi(d1) : lo(d1), d2s = s ? hi(d2) : lo(d2);
-                be_boundary_backward1(d1s, d2s, s ? hi(lb) : lo(lb), s ? hi(glb) : lo(glb), &gb1[s], &gb2[s]);
-                const int mk = be_mask(d1s, d2s, false);                                       // global_training.py:84-90,121-127
-                const bool on = (zgv[s] != 0.0f) && (mk != 0);
-                const float e2 = on ? (((mk == 1) ? P.z[0] : P.z[1]) - zgv[s]) : 0.0f;
-                l6[s] = e2 * e2;
-                const float ge = on ? 2.0f * kd * e2 : 0.0f;          // select, not multiply: kd is inf when the batch mask is empty
-                s12[s] = (mk == 1) ? ge : 0.0f;
-                s13[s] = (mk == 1) ? 0.0f : ge;
-            }
-            lossacc[6] += fold(mk2(l6[0], l6[1]));
-            sums[12] = mk2(s12[0], s12[1]); sums[13] = mk2(s13[0], s13[1]);
-            gd1 = add2(gd1, mk2(gb1[0], gb1[1])); gd2 = add2(gd2, mk2(gb2[0], gb2[1]));
-            be_wedge_backward2(P, 0, X, Y, g.w, gd1, &sums[0]);
-            be_wedge_backward2(P, 1, X, Y, g.w, gd2, &sums[4]);
+            for (int i = 0; i < 4; ++i) { sums[i] = mul2(gd1, coef1[i]); sums[4 + i] = mul2(gd2, coef2[i]); }
             float ssum[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) ssum[i] = (i < 14) ? fold(sums[i]) : 0.0f;
-            const float tot = warp_reduce16(ssum, lane);
-            if (!(lane & 1)) s_part3[warp][lane >> 1] = tot;
+            {   // row of this lane, float4 columns rotated by (lane >> 1): conflict-free 16-byte stores and helper loads
+                float4* row = s_partB + (warp * 32 + lane) * 4;
+                const int rot = lane >> 1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) row[(c + rot) & 3] = make_float4(ssum[4 * c], ssum[4 * c + 1], ssum[4 * c + 2], ssum[4 * c + 3]);
+            }
         }
+        bar_arrive_id<BAR_SUMS, NTHR>();
     }
-    __syncthreads();
-    if (warp == 0) chain(n - 1);
 
     // ---------------- per-CTA partial loss sums ----------------
     {
@@ -447,6 +549,7 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) sums[i] = (i < 7) ? lossacc[i] : 0.0f;
         const float tot = warp_reduce16(sums, lane);
+        __syncthreads();
         if (!(lane & 1)) s_part[warp][lane >> 1] = tot;
         __syncthreads();
         if (tid < 8) {
@@ -462,7 +565,13 @@ __global__ void __maxnreg__(128) be_loss2_kernel(const BeLossArgs a) {
 
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    if (a.g.R == 21) be_loss2_kernel<21><<<grid, NT, 0, st>>>(a);
-    else be_loss2_kernel<0><<<grid, NT, 0, st>>>(a);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(be_loss2_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
+        cudaFuncSetAttribute(be_loss2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
+        configured = true;
+    }
+    if (a.g.R == 21) be_loss2_kernel<21><<<grid, NTHR, DYN_SMEM, st>>>(a);
+    else be_loss2_kernel<0><<<grid, NTHR, DYN_SMEM, st>>>(a);
     ++g_be_launches;
 }
