@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     __shared__ __align__(16) float s_crec[2][BE_CREC];
     __shared__ float s_axis[BE_MAX_R + 3];
     __shared__ float s_part[BE_WARPS][16];          // end of kernel: loss partial sums per warp
-    __shared__ __align__(16) float s_VS[16];        // V[9], S[6] of the current patch (helper -> render warps)
+    __shared__ __align__(16) float s_VS[12];        // (V_k - V_0)[3], (S_k - S_0)[3] for k = 1, 2 of the current patch (helper -> render warps)
     __shared__ unsigned long long s_vready;         // mbarrier: s_VS published
     // Stencil exchange planes in PAIR layout: entry e holds, per channel, (value at pixel e-HALO, value at pixel e-HALO+NT), so the
     // neighbour of both slots of thread t at offset `off` is the one entry t+HALO+off (3 LDS.128 for 6 channels of two pixels).
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     extern __shared__ float4 s_dyn[];             // 69 KB: above the 48 KB static limit
     float4* const s_X = s_dyn;                    // [9][NE]
     float4* const s_P2 = s_X;                     // [3][NE] (2 used) wedge weights of the rendered patch: (u1, u2) image 1, (u1, u2) image 2
-    float4* const s_G2 = s_X + 3 * NE;            // [6][NE] Sobel gradients: gx (c0,c1) (c2,c3) (c4,c5), gy (c0,c1) (c2,c3) (c4,c5)
+    float4* const s_G2 = s_X + 3 * NE;            // [6][NE] (4 used) projected Sobel gradients: PX (img 1), PX (img 2), PY (img 1), PY (img 2)
     float4* const s_partA = s_X + 9 * NE;         // [7*32][3] per-lane A^T G partial sums (9 of 12 floats used), rows of 48 bytes
     float4* const s_partB = s_partA + BE_WARPS * 32 * 3;   // [7*32][4] per-lane backward sums (14 of 16 used), rows of 64 bytes, swizzled
     float4* const s_stash0 = s_partB + BE_WARPS * 32 * 4;  // [NT] thread-private (d1, d2) pairs, stage A -> D
@@ -165,10 +165,11 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                     for (int c = 0; c < 3; ++c) sacc += V[3 * pi_[i] + c] * C[3 * pj_[i] + c] + C[3 * pi_[i] + c] * V[3 * pj_[i] + c];
                     Ssym[i] = sacc;
                 }
-                if (lane == 0) {
+                if (lane == 0) {   // V_k - V_0 and S_k - S_0 (k = 1, 2): all the per-pixel backward needs (u_0 = 1 - u_1 - u_2)
                     float4* o = reinterpret_cast<float4*>(s_VS);
-                    o[0] = make_float4(V[0], V[1], V[2], V[3]); o[1] = make_float4(V[4], V[5], V[6], V[7]);
-                    o[2] = make_float4(V[8], Ssym[0], Ssym[1], Ssym[2]); o[3] = make_float4(Ssym[3], Ssym[4], Ssym[5], 0.0f);
+                    o[0] = make_float4(V[3] - V[0], V[4] - V[1], V[5] - V[2], V[6] - V[0]);
+                    o[1] = make_float4(V[7] - V[1], V[8] - V[2], Ssym[1] - Ssym[0], Ssym[3] - Ssym[1]);
+                    o[2] = make_float4(Ssym[4] - Ssym[2], Ssym[2] - Ssym[0], Ssym[4] - Ssym[1], Ssym[5] - Ssym[2]);
                 }
             }
             __syncwarp();
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                     }
                 }
             f2 sx[6], sy[6];
+            float D1[3], D2[3];
             {
-                float D1[3], D2[3];
                 const float* cc = s_crec[cur];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { D1[c] = cc[3 + c] - cc[c]; D2[c] = cc[6 + c] - cc[c]; }
@@ -394,33 +395,19 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             }
             lossacc[3] = fmaf(lo(l3), lo(mI), fmaf(hi(l3), hi(mI), lossacc[3]));
             lossacc[4] = fmaf(lo(l4), lo(mI), fmaf(hi(l4), hi(mI), lossacc[4]));
-            store_pairs(s_G2, gxy, 12);
-        }
-        bar_sync_id<BAR_RENDER, NT>();   // (X2) Sobel gradients visible
-
-        // ---------------- stage C: Sobel adjoint into G, A^T G partial sums -> helper ----------------
-        {
+            // What the rest of the backward pass needs from the adjoint of the Sobel filter, A_c = K^T (gx_c, gy_c):
+            //  * dL/du_1 - dL/du_0 and dL/du_2 - dL/du_0 use sum_c A_c (C_k - C_0)_c = K^T applied to the PROJECTED fields
+            //    sum_c (C_k - C_0)_c gx_c, sum_c (C_k - C_0)_c gy_c: 8 values per pixel go through shared memory instead of 12;
+            //  * A^T G uses sum_p u_w(p) A_c(p) = sum_q gx_c(q) Sobel_x(u_w)(q) + gy_c(q) Sobel_y(u_w)(q), which is local to q.
+            f2 proj[8];                              // (PX1, PX2) image 1, (PX1, PX2) image 2, then the same for PY
 #pragma unroll
-            for (int di = -1; di <= 1; ++di)
-#pragma unroll
-                for (int dj = -1; dj <= 1; ++dj) {
-                    if (di == 0 && dj == 0) continue;
-                    const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
-                    const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
-                    const float4* pn = s_G2 + (tid + HALO + di * R + dj);
-                    if (wx != 0.0f) {
-                        const float4 v0 = pn[0], v1 = pn[NE], v2 = pn[2 * NE];
-                        G[0] = fma2(bc2(wx), mk2(v0.x, v0.y), G[0]); G[1] = fma2(bc2(wx), mk2(v0.z, v0.w), G[1]);
-                        G[2] = fma2(bc2(wx), mk2(v1.x, v1.y), G[2]); G[3] = fma2(bc2(wx), mk2(v1.z, v1.w), G[3]);
-                        G[4] = fma2(bc2(wx), mk2(v2.x, v2.y), G[4]); G[5] = fma2(bc2(wx), mk2(v2.z, v2.w), G[5]);
-                    }
-                    if (wy != 0.0f) {
-                        const float4 v0 = pn[3 * NE], v1 = pn[4 * NE], v2 = pn[5 * NE];
-                        G[0] = fma2(bc2(wy), mk2(v0.x, v0.y), G[0]); G[1] = fma2(bc2(wy), mk2(v0.z, v0.w), G[1]);
-                        G[2] = fma2(bc2(wy), mk2(v1.x, v1.y), G[2]); G[3] = fma2(bc2(wy), mk2(v1.z, v1.w), G[3]);
-                        G[4] = fma2(bc2(wy), mk2(v2.x, v2.y), G[4]); G[5] = fma2(bc2(wy), mk2(v2.z, v2.w), G[5]);
-                    }
-                }
+            for (int m = 0; m < 2; ++m) {
+                proj[2 * m] = fma2(gxy[3 * m], bc2(D1[0]), fma2(gxy[3 * m + 1], bc2(D1[1]), mul2(gxy[3 * m + 2], bc2(D1[2]))));
+                proj[2 * m + 1] = fma2(gxy[3 * m], bc2(D2[0]), fma2(gxy[3 * m + 1], bc2(D2[1]), mul2(gxy[3 * m + 2], bc2(D2[2]))));
+                proj[4 + 2 * m] = fma2(gxy[6 + 3 * m], bc2(D1[0]), fma2(gxy[7 + 3 * m], bc2(D1[1]), mul2(gxy[8 + 3 * m], bc2(D1[2]))));
+                proj[5 + 2 * m] = fma2(gxy[6 + 3 * m], bc2(D2[0]), fma2(gxy[7 + 3 * m], bc2(D2[1]), mul2(gxy[8 + 3 * m], bc2(D2[2]))));
+            }
+            store_pairs(s_G2, proj, 8);
             f2 sums[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) sums[i] = bc2(0.0f);
@@ -428,17 +415,45 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             for (int m = 0; m < 2; ++m) {
                 const f2 gg = sub2(bc2(1.0f), h[2 * m + 1]);
                 const f2 u[3] = {mul2(sub2(bc2(1.0f), h[2 * m]), gg), mul2(h[2 * m], gg), h[2 * m + 1]};
+                const f2 UX[3] = {neg2(add2(ux[2 * m], ux[2 * m + 1])), ux[2 * m], ux[2 * m + 1]};      // Sobel(u0) = -Sobel(u1) - Sobel(u2)
+                const f2 UY[3] = {neg2(add2(uy[2 * m], uy[2 * m + 1])), uy[2 * m], uy[2 * m + 1]};
 #pragma unroll
                 for (int wd = 0; wd < 3; ++wd)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) sums[3 * wd + c] = fma2(u[wd], G[3 * m + c], sums[3 * wd + c]);
+                    for (int c = 0; c < 3; ++c)
+                        sums[3 * wd + c] = fma2(u[wd], G[3 * m + c], fma2(UX[wd], gxy[3 * m + c], fma2(UY[wd], gxy[6 + 3 * m + c], sums[3 * wd + c])));
             }
             float4* row = s_partA + (warp * 32 + lane) * 3;
             row[0] = make_float4(fold(sums[0]), fold(sums[1]), fold(sums[2]), fold(sums[3]));
             row[1] = make_float4(fold(sums[4]), fold(sums[5]), fold(sums[6]), fold(sums[7]));
             row[2] = make_float4(fold(sums[8]), 0.0f, 0.0f, 0.0f);
         }
-        bar_arrive_id<BAR_ATG, NTHR>();
+        bar_arrive_id<BAR_ATG, NTHR>();  // A^T G partial sums handed to the helper
+        bar_sync_id<BAR_RENDER, NT>();   // (X2) projected Sobel gradients visible
+
+        // ---------------- stage C: adjoint of the Sobel filter on the projected fields ----------------
+        f2 AE[4];                                    // sum_c A_c (C_k - C_0)_c for (k = 1, 2) of image 1, then of image 2
+#pragma unroll
+        for (int i = 0; i < 4; ++i) AE[i] = bc2(0.0f);
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                if (di == 0 && dj == 0) continue;
+                const float wx = (float)(-dj * ((di == 0) ? 2 : 1));   // weight of gx(i+di, j+dj) in dL/dP(i,j)
+                const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
+                const float4* pn = s_G2 + (tid + HALO + di * R + dj);
+                if (wx != 0.0f) {
+                    const float4 v0 = pn[0], v1 = pn[NE];
+                    AE[0] = fma2(bc2(wx), mk2(v0.x, v0.y), AE[0]); AE[1] = fma2(bc2(wx), mk2(v0.z, v0.w), AE[1]);
+                    AE[2] = fma2(bc2(wx), mk2(v1.x, v1.y), AE[2]); AE[3] = fma2(bc2(wx), mk2(v1.z, v1.w), AE[3]);
+                }
+                if (wy != 0.0f) {
+                    const float4 v0 = pn[2 * NE], v1 = pn[3 * NE];
+                    AE[0] = fma2(bc2(wy), mk2(v0.x, v0.y), AE[0]); AE[1] = fma2(bc2(wy), mk2(v0.z, v0.w), AE[1]);
+                    AE[2] = fma2(bc2(wy), mk2(v1.x, v1.y), AE[2]); AE[3] = fma2(bc2(wy), mk2(v1.z, v1.w), AE[3]);
+                }
+            }
 
         // ---------------- stage D: per-pixel backward -> 14 per-patch sums -> helper ----------------
         {
@@ -457,13 +472,8 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             }
             const float4 sd = s_stash0[tid], sg = s_stash1[tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);
-            // -- part 1: everything that does not depend on V, S (runs while the helper reduces and solves) --
+            // -- part 1: boundary and depth terms, which do not depend on V, S (the helper has had stage C to reduce and solve) --
             f2 sums[14];
-            f2 coef1[4], coef2[4];                 // d(sums[0..3]) / d gd1 and d(sums[4..7]) / d gd2: the edge geometry of the two wedges
-#pragma unroll
-            for (int i = 0; i < 4; ++i) coef1[i] = coef2[i] = bc2(0.0f);
-            be_wedge_backward2(P, 0, X, Y, g.w, bc2(1.0f), coef1);
-            be_wedge_backward2(P, 1, X, Y, g.w, bc2(1.0f), coef2);
             const f2 lb = be_boundary2(d1, d2);
             const f2 bl = mul2(bdv, lb);
             lossacc[5] += fold(mul2(bl, bl));
@@ -491,12 +501,14 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             }
             // -- part 2: the ridge backward through V, S --
             mbar_wait(&s_vready, (unsigned)(k & 1));
-            float V[9], Sm[9];
+            float DV[2][3], DS[2][3], D1[3], D2[3];     // V_k - V_0, S_k - S_0 (k = 1, 2; from the helper), C_k - C_0
             {
                 const float4* vs = reinterpret_cast<const float4*>(s_VS);
-                const float4 v0 = vs[0], v1 = vs[1], v2 = vs[2], v3 = vs[3];
-                V[0] = v0.x; V[1] = v0.y; V[2] = v0.z; V[3] = v0.w; V[4] = v1.x; V[5] = v1.y; V[6] = v1.z; V[7] = v1.w; V[8] = v2.x;
-                Sm[0] = v2.y; Sm[1] = v2.z; Sm[2] = v2.w; Sm[3] = v2.z; Sm[4] = v3.x; Sm[5] = v3.y; Sm[6] = v2.w; Sm[7] = v3.y; Sm[8] = v3.z;
+                const float4 v0 = vs[0], v1 = vs[1], v2 = vs[2];
+                DV[0][0] = v0.x; DV[0][1] = v0.y; DV[0][2] = v0.z; DV[1][0] = v0.w; DV[1][1] = v1.x; DV[1][2] = v1.y;
+                DS[0][0] = v1.z; DS[0][1] = v1.w; DS[0][2] = v2.x; DS[1][0] = v2.y; DS[1][1] = v2.z; DS[1][2] = v2.w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { D1[c] = C[3 + c] - C[c]; D2[c] = C[6 + c] - C[c]; }
             }
 #pragma unroll
             for (int i = 8; i < 12; ++i) sums[i] = bc2(0.0f);
@@ -505,23 +517,24 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 const f2 h1 = h[2 * m], h2 = h[2 * m + 1];
                 const f2 gg = sub2(bc2(1.0f), h2), g1 = sub2(bc2(1.0f), h1);
                 const f2 u[3] = {mul2(g1, gg), mul2(h1, gg), h2};
-                f2 gu[3];
+                // E_k = dL/du_k - dL/du_0 = sum_c (G_c + A_c)(C_k - C_0)_c + y_c (V_k - V_0)_c - ((S_k - S_0) u)     (be_ridge_backward_pixel)
+                f2 E[2];
 #pragma unroll
-                for (int wd = 0; wd < 3; ++wd) {
-                    // dL/du_w = sum_c (G_c C[w][c] + y_c V[w][c]) - (S u)_w     (be_ridge_backward_pixel)
+                for (int kk = 0; kk < 2; ++kk) {
+                    const float* Dk = kk ? D2 : D1;
                     float yv[2];
 #pragma unroll
                     for (int s = 0; s < 2; ++s)
-                        yv[s] = fmaf(ny[s][3 * m], V[3 * wd], fmaf(ny[s][3 * m + 1], V[3 * wd + 1], ny[s][3 * m + 2] * V[3 * wd + 2]));
-                    f2 t = mk2(yv[0], yv[1]);
+                        yv[s] = fmaf(ny[s][3 * m], DV[kk][0], fmaf(ny[s][3 * m + 1], DV[kk][1], ny[s][3 * m + 2] * DV[kk][2]));
+                    f2 t = add2(AE[2 * m + kk], mk2(yv[0], yv[1]));
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) t = fma2(G[3 * m + c], bc2(C[3 * wd + c]), t);
+                    for (int c = 0; c < 3; ++c) t = fma2(G[3 * m + c], bc2(Dk[c]), t);
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) t = fma2(u[v], bc2(-Sm[3 * wd + v]), t);
-                    gu[wd] = t;
+                    for (int v = 0; v < 3; ++v) t = fma2(u[v], bc2(-DS[kk][v]), t);
+                    E[kk] = t;
                 }
-                const f2 gh1 = mul2(gg, sub2(gu[1], gu[0]));                                   // be_wedges_backward
-                const f2 gh2 = sub2(gu[2], fma2(g1, gu[0], mul2(h1, gu[1])));
+                const f2 gh1 = mul2(gg, E[0]);                                                 // be_wedges_backward
+                const f2 gh2 = sub2(E[1], mul2(h1, E[0]));
                 f2 da, de;
                 be_h_grad2(d1, P.inv_eta[2 * m], &da, &de);
                 gd1 = fma2(gh1, da, gd1); sums[8 + 2 * m] = fma2(gh1, de, sums[8 + 2 * m]);
@@ -529,7 +542,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 gd2 = fma2(gh2, da, gd2); sums[9 + 2 * m] = fma2(gh2, de, sums[9 + 2 * m]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { sums[i] = mul2(gd1, coef1[i]); sums[4 + i] = mul2(gd2, coef2[i]); }
+            for (int i = 0; i < 8; ++i) sums[i] = bc2(0.0f);
+            be_wedge_backward2(P, 0, X, Y, g.w, gd1, &sums[0]);
+            be_wedge_backward2(P, 1, X, Y, g.w, gd2, &sums[4]);
             float ssum[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) ssum[i] = (i < 14) ? fold(sums[i]) : 0.0f;
