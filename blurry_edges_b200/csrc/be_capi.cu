@@ -384,6 +384,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
     BE_REQUIRE(c->gtable, "be_global_loss_stage1 must run first");
     BE_REQUIRE(global_patches > 0, "global_patches must be positive");
+    BE_REQUIRE((double)B * c->g.H * c->g.W * BE_TW < 4.0e9, "batch of %d %dx%d pairs exceeds the 32-bit target offsets of the loss kernel", B, c->g.H, c->g.W);
     cudaStream_t st = (cudaStream_t)stream;
     const BeGeom& g = c->g;
     const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)global_patches;

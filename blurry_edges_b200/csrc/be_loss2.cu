@@ -245,11 +245,11 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
         }
     };
     const f2 mI = mk2(interior[0] ? 1.0f : 0.0f, interior[1] ? 1.0f : 0.0f);
-    const f2 kIs = mul2(bc2(2.0f * a.ks), mI), kIsc = mul2(bc2(2.0f * a.ksc), mI);    // Sobel-loss weights, zero off the interior
     const f2 Y = mk2(s_axis[pi[0]], s_axis[pi[1]]), X = mk2(s_axis[pj[0]], s_axis[pj[1]]);
     const float vm0 = (RCT == BE_MAX_R || valid[0]) ? 1.0f : 0.0f, vm1 = valid[1] ? 1.0f : 0.0f;   // R = 21: every thread has a low pixel
     const float kd = a.gamma_d / (float)(*a.mask_count);
-    const size_t TPS = (size_t)a.NB * g.H * g.W * 4;      // floats between consecutive float4 planes of T
+    const unsigned TPS = (unsigned)a.NB * g.H * g.W * 4;   // floats between consecutive float4 planes of T (32-bit offsets: be_launch_loss2 checks the size)
+    const unsigned toff0[2] = {(unsigned)((((size_t)b * g.H + y0 + pi[0]) * g.W + pj[0]) * 4), (unsigned)((((size_t)b * g.H + y0 + pi[1]) * g.W + pj[1]) * 4)};
     const float k2c = 2.0f * a.kc, k2cc = 2.0f * a.kcc;
 
     float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
 
     for (int k = 0; k < n; ++k) {
         const int cur = k & 1;
-        const int x0 = (px0 + k) * g.stride;
+        const unsigned x0 = (unsigned)((px0 + k) * g.stride);
         auto load_patch = [&](BePatch& P) {
             const float4* q4 = reinterpret_cast<const float4*>(s_rec[cur]);
             const float4 r0 = q4[0], r1 = q4[1], r2 = q4[2], r3 = q4[3], r4 = q4[4];
@@ -273,9 +273,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
             C[8] = s_crec[cur][8];
         };
-        const float* tp[2];      // plane 0 of each slot's pixel in the packed targets
-#pragma unroll
-        for (int s = 0; s < 2; ++s) tp[s] = a.T + (((size_t)b * g.H + y0 + pi[s]) * g.W + x0 + pj[s]) * 4;
+        const unsigned tp[2] = {toff0[0] + 4u * x0, toff0[1] + 4u * x0};      // element offset of plane 0 of each slot's pixel in the packed targets
 
         // ---------------- stage A: distances, soft indicators, render, direct dL/dP ----------------
         f2 h[4], G[6];
@@ -288,10 +286,10 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float4 t2[2], t3[2], t4[2];                  // targets: issued before the arithmetic that hides their latency
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                t1[s] = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS + 2));
-                t2[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 2 * TPS));
-                t3[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 3 * TPS));
-                t4[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 4 * TPS));
+                t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS + 2u)));
+                t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 2u * TPS)));
+                t3[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 3u * TPS)));
+                t4[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 4u * TPS)));
             }
             f2 d1, d2;
             be_pixel_dists2(P, X, Y, g.w, &d1, &d2);
@@ -341,9 +339,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float4 t6[2], t7[2], t8[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                t6[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 6 * TPS));
-                t7[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 7 * TPS));
-                t8[s] = __ldg(reinterpret_cast<const float4*>(tp[s] + 8 * TPS));
+                t6[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 6u * TPS)));
+                t7[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 7u * TPS)));
+                t8[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 8u * TPS)));
             }
             f2 ux[4], uy[4];                           // Sobel responses of (u1, u2) of image 1 and of image 2
 #pragma unroll
@@ -389,7 +387,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 const f2 e1 = mk2(lo(mag) - dgt[0][c], hi(mag) - dgt[1][c]), e2 = mk2(lo(mag) - dgi[0][c], hi(mag) - dgi[1][c]);
                 l3 = fma2(e1, e1, l3);
                 l4 = fma2(e2, e2, l4);
-                const f2 gm = mul2(fma2(kIsc, e2, mul2(kIs, e1)), ir);         // zero off the interior
+                const f2 gm = mul2(mul2(fma2(bc2(2.0f * a.ksc), e2, mul2(bc2(2.0f * a.ks), e1)), mI), ir);   // zero off the interior
                 gxy[c] = mul2(gm, sx[c]);
                 gxy[6 + c] = mul2(gm, sy[c]);
             }
@@ -465,10 +463,10 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float zgv[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp[s]));
-                const float2 q1 = __ldg(reinterpret_cast<const float2*>(tp[s] + TPS));
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
+                const float2 q1 = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
                 ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
-                zgv[s] = __ldg(tp[s] + 5 * TPS);
+                zgv[s] = __ldg(a.T + (tp[s] + 5u * TPS));
             }
             const float4 sd = s_stash0[tid], sg = s_stash1[tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);
