@@ -272,9 +272,9 @@ def extra_configs(args, rank, world, dev, barrier):
     ms = _timed(train_step2, steps, 3, dev, barrier, world)
     out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
                              'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2,
-                             'kernels_ncu': {'be_loss2_kernel': {'ms': 2.59, 'warp_inst_per_patch': 11293, 'issue_active': 0.50},
-                                             'be_run3_kernel<TRAINFWD>': {'ms': 0.59, 'warp_inst_per_patch': 3273, 'issue_active': 0.65},
-                                             'source': 'profiles/r1j_train_kernels_full.txt'},
+                             'kernels_ncu': {'be_loss2_kernel': {'ms': 2.30, 'warp_inst_per_patch': 9519, 'issue_active': 0.48, 'l1_smem_pipe': 0.69},
+                                             'be_run3_kernel<TRAINFWD>': {'ms': 0.60, 'warp_inst_per_patch': 3273, 'issue_active': 0.65, 'l1_smem_pipe': 0.69},
+                                             'source': 'profiles/r1k_train_kernels_full.txt'},
                              'algorithmic_bytes_per_patch': 810.0,
                              'hbm_frac_at_algorithmic_bytes': 810.0 * Bt2 * L / (ms / 1e3) / 1e9 / peaks()[0]}
     del crit2, raw2, img2, gt2, bd2, deri2, zg2
