@@ -11,8 +11,13 @@
 //     parameters, and prefetches the next patch's records.  The render warps hand over with bar.arrive (non-blocking) and wait
 //     for V, S on an mbarrier, behind the part of the backward pass that does not depend on them (edge geometry, boundary and
 //     depth terms); the two remaining barriers (the Sobel stencil exchanges) are named barriers of the render warps only;
-//   * the Sobel stages exchange neighbours through shared memory in PAIR layout (see s_X below) so that their FMAs are packed too;
-//     R = 21 is a template constant (neighbour offsets become immediates).
+//   * the kernel is bound by the L1/shared-memory data pipe, so the stencil stages move as little as the algebra allows: the
+//     forward Sobel runs on the wedge weights u1, u2 of the two images (the filter is linear, P_c = C0_c + u1 (C1-C0)_c +
+//     u2 (C2-C0)_c: 4 values per neighbour instead of 6 channels), the adjoint on the gradients projected onto C1-C0 and C2-C0
+//     (only dL/du_k - dL/du_0 enters the backward: 8 values instead of 12), and the adjoint's share of A^T G is accumulated
+//     locally (sum_q gx_c(q) Sobel_x(u_w)(q) + gy_c(q) Sobel_y(u_w)(q)).  Neighbours are exchanged in PAIR layout (see s_X below)
+//     so that the stencil FMAs are packed too; R = 21 is a template constant (neighbour offsets become immediates); targets
+//     are addressed with 32-bit offsets (no spills at 128 registers).
 #include "be_internal.h"
 #include "be_pack.cuh"
 
