@@ -33,7 +33,7 @@ import torch  # noqa: E402
 S, R, STRIDE = 147, 21, 2
 HP = (S - R) // STRIDE + 1
 L = HP * HP
-METRIC = 'patches/sec render+fold+depth (inference pass B)'
+METRIC = 'patches/sec render+fold+depth (BASELINE configs[1]: inference pass B; the fwd+bwd figures are under train_step*)'
 UNIT = 'patches/s'
 # algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
 # params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
