@@ -205,6 +205,21 @@ def run_reference(args, rank, world):
                             'sample': f'{pairs} pairs/step x {args.steps} steps, torch {torch.__version__} eager fp32 CPU, '
                                       'oracle/be_oracle.py restatement of the reference (one pair per call, as the reference helper)'},
            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    try:   # the fwd+bwd side of the metric: GlobalLoss forward + autograd backward of the same CPU port, one pair (bounded sample)
+        import synth
+        from oracle import be_oracle as O
+        g, cam = O.Geometry(H=S, W=S), O.Camera()
+        raw = synth.raw_global(1, L, seed=300).requires_grad_(True)
+        img_t = synth.image_pairs(1, S, S, seed=301)
+        gt, bd, deri, zg = synth.loss_targets(1, S, S, seed=302)
+        gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 1e-4]          # gamma_idx = 0 (global_training.py:28-51)
+        t0 = time.perf_counter()
+        O.global_loss(raw, img_t, gt, bd, deri, zg, gam, g, cam, trace_form=True).backward()
+        dt2 = time.perf_counter() - t0
+        out['train_step'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss, CPU port, autograd)', 'value': L / dt2, 'unit': UNIT,
+                             'sample': '1 pair, 1 repetition', 'seconds': dt2}
+    except Exception as e:
+        out['train_step'] = {'error': str(e)[:120]}
     _emit(out)
 
 
