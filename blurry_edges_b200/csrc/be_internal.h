@@ -89,6 +89,19 @@ void be_launch_cover_count(const BeGeom& g, float* out, cudaStream_t st);
 
 extern long long g_be_launches;
 
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so it is remembered per
+// device: a process that drives several GPUs (one context each) configures every one of them on its first launch there.
+constexpr int BE_MAX_DEVICES = 64;
+template <typename Kernel>
+inline void be_opt_in_smem(Kernel kernel, size_t bytes, bool (&done)[BE_MAX_DEVICES]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool known = dev >= 0 && dev < BE_MAX_DEVICES;
+    if (known && done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (known) done[dev] = true;
+}
+
 // method-granularity ops (be_ops.cu)
 void be_op_params2dists(const float* params, int K, int B, size_t Lsp, int R, float w, float* dists, cudaStream_t st);
 void be_op_params2dists_bwd(const float* params, int K, const float* gd, int B, size_t Lsp, int R, float w, float* gp, cudaStream_t st);

@@ -583,12 +583,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
 
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(be_loss2_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
-        cudaFuncSetAttribute(be_loss2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM);
-        configured = true;
-    }
+    static bool configured21[BE_MAX_DEVICES] = {}, configured0[BE_MAX_DEVICES] = {};
+    be_opt_in_smem(be_loss2_kernel<21>, DYN_SMEM, configured21);
+    be_opt_in_smem(be_loss2_kernel<0>, DYN_SMEM, configured0);
     if (a.g.R == 21) be_loss2_kernel<21><<<grid, NTHR, DYN_SMEM, st>>>(a);
     else be_loss2_kernel<0><<<grid, NTHR, DYN_SMEM, st>>>(a);
     ++g_be_launches;

@@ -426,11 +426,8 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
 
 template <int MODE>
 static void launch3(const BeRunArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(be_run3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<MODE>::bytes);
-        configured = true;
-    }
+    static bool configured[BE_MAX_DEVICES] = {};
+    be_opt_in_smem(be_run3_kernel<MODE>, Smem<MODE>::bytes, configured);
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
     be_run3_kernel<MODE><<<grid, NTHR, Smem<MODE>::bytes, st>>>(a);
 }
