@@ -77,6 +77,11 @@ class ClockSampler:
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
+            # the first NVML queries of a process take milliseconds (longer when several ranks ask at once): pay for them here,
+            # not inside the timed region
+            pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
         except Exception:
             self.nvml = None
 
@@ -138,7 +143,7 @@ class ClockSampler:
         if self.nvml is not None:
             sm = sorted(self.sm)
             return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
-                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 2 ms period'}
+                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 2 ms period, over the device-resident and the e2e timed regions'}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -355,6 +360,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     B = args.pairs
+    # one rank per GPU on a multi-socket box: keep the rank (and, first-touch, its pinned buffers) on the GPU's NUMA node
+    from blurry_edges_b200.dist_utils import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa) else {'bound': False}
     global TRAFFIC_NCU
     TRAFFIC_NCU = TRAFFIC_NCU_64 if B == 64 else None
     est_h, img_h = make_inputs(B, seed=100 + rank)
@@ -392,19 +400,20 @@ def run_ours(args, rank, world, local_rank):
             kern.append(ctx.last_timing())                         # waits for this step's last kernel
         barrier()
         t_wall = time.perf_counter() - t_wall
-    launches = _lib.launch_count() - n0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    ctx.set_timing(False)
+        launches = _lib.launch_count() - n0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        ctx.set_timing(False)
 
-    # end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H of the maps
-    for _ in range(max(1, args.warmup // 2)):
-        ctx.host_render_fold(est_h, img_h, layout, out=host_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.host_render_fold(est_h, img_h, layout, out=host_out)   # synchronises internally
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        # end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H of the maps
+        # (still inside the clock sampler: both timed regions are covered)
+        for _ in range(max(1, args.warmup // 2)):
+            ctx.host_render_fold(est_h, img_h, layout, out=host_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.host_render_fold(est_h, img_h, layout, out=host_out)   # synchronises internally
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     extra = {} if args.no_extra else extra_configs(args, rank, world, dev, barrier)
 
@@ -431,7 +440,8 @@ def run_ours(args, rank, world, local_rank):
            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(B * (L * 12 + 6 * S * S) * 4),
                    'd2h_bytes_per_step': int(B * 15 * S * S * 4), 'ms_per_step': e2e_ms / args.steps,
                    'api': 'be_host_render_fold (pinned host buffers, synchronous): est + image pair in, the six maps of '
-                          'PostProcess.forward (15 planes, blurry_edges_test.py:100) out'},
+                          'PostProcess.forward (15 planes, blurry_edges_test.py:100) out',
+                   'numa_binding_rank0': numa},
            'gpu_launches': int(launches),
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                         'traffic': TRAFFIC_NCU, 'kernel': 'be_run3_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
@@ -511,6 +521,7 @@ def main():
     ap.add_argument('--ref-pairs', type=int, default=8, help='pairs per step of the CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (train step, densify w, big image)')
+    ap.add_argument('--no-numa', action='store_true', help='multi-rank runs: do not bind each rank to the CPUs of its GPU\'s NUMA node')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))

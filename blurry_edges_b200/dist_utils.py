@@ -1,6 +1,8 @@
 """The two collectives of the path, kept separate so that the CPU test-suite can run them under gloo."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -22,3 +24,60 @@ def reduce_accumulator(acc: torch.Tensor, group=None, dst_group_rank: int = 0):
         dst = dist.get_global_rank(group, dst_group_rank) if group is not None else dst_group_rank
         dist.reduce(acc, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return acc
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs next to GPU `device_index` (NVML CPU affinity, else the sysfs `local_cpulist` of the PCI device),
+    intersected with the CPUs the process may use.  Call it BEFORE allocating pinned host buffers: they are then placed
+    first-touch on the GPU's own NUMA node, so the H2D / D2H traffic of the host-buffer entry point (be_host_render_fold) does not
+    cross the socket interconnect when one rank per GPU runs on a multi-socket box.  Never raises; returns what it did."""
+    info = {'device': device_index, 'bound': False}
+    try:
+        allowed = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        return info
+    cpus = set()
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (max(allowed) // 64) + 1
+        for w, bits in enumerate(pynvml.nvmlDeviceGetCpuAffinity(h, words)):
+            cpus |= {64 * w + b for b in range(64) if (int(bits) >> b) & 1}
+        info['source'] = 'nvml'
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            with open(f'/sys/bus/pci/devices/{bus[-12:]}/numa_node') as f:
+                info['numa_node'] = int(f.read())
+        except Exception:
+            pass
+    except Exception:
+        cpus = set()
+    if not cpus:
+        try:
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+            dev = torch.cuda.get_device_properties(device_index).pci_device_id
+            with open(f'/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist') as f:
+                for part in f.read().strip().split(','):
+                    lo, _, hi = part.partition('-')
+                    cpus |= set(range(int(lo), int(hi or lo) + 1))
+            info['source'] = 'sysfs'
+        except Exception:
+            return info
+    use = cpus & allowed
+    if not use or use == allowed:
+        info['cpus'] = len(allowed)
+        return info                      # single node, or an affinity mask that does not overlap what we may use
+    try:
+        os.sched_setaffinity(0, use)
+        info.update(bound=True, cpus=len(use))
+    except OSError:
+        pass
+    return info
