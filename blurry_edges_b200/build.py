@@ -33,7 +33,8 @@ def stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, '-o', LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get('BE_NVCC_EXTRA', '').split()          # experiments: e.g. BE_NVCC_EXTRA=-DBE_LOSS2_RING=0
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, '-o', LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
