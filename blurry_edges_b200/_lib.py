@@ -303,6 +303,9 @@ class Context:
             check(self.lib.be_global_loss_stage1(self.h, _ptr(raw), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri),
                                                  _ptr(bndry_depth), B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()),
                                                  _stream(self.device)))
+        # the C side compares the two device pointers the same way (be_global_loss_stage1): the training call of the reference
+        # passes one tensor twice (global_training.py:210) and gets the kernel variant that skips the GT target planes
+        self.last_same_gt = img_ny.data_ptr() == img_gt.data_ptr()
         return gimg, gbnd, cnt
 
     def global_loss_stage2(self, B, gammas, global_patches, mask_count, want_grad=True):

@@ -64,6 +64,7 @@ struct be_ctx {
     float* crec;        // [max_batch*L][BE_CREC]
     float* T;           // [max_batch][H][W][BE_TW]
     float* partials;    // [max_batch*Hp*runs][8]
+    int same_gt;        // the last be_global_loss_stage1 call had img_gt == img_ny
     size_t train_bytes;
     // optional per-kernel timing of the last be_render_fold_fwd call (be_ctx_set_timing)
     int timing;
@@ -372,6 +373,7 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     launch_run(BE_RUN_TRAINFWD, a, st);
     be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
     be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
+    c->same_gt = (dev_img_gt == dev_img_ny);
     BE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -392,7 +394,7 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.gtable = c->gtable; a.crec = c->crec; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
     a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
-    a.g = g; a.NB = B;
+    a.g = g; a.NB = B; a.same_gt = c->same_gt;
     pick_runs(g, B, LOSS_CTAS, LOSS_OVH, &a.G, &a.runs_per_row);
     BeLossScale sc;
     memset(&sc, 0, sizeof(sc));

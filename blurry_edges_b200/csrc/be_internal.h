@@ -12,7 +12,7 @@ constexpr int BE_REC = 32;            // floats per patch-table record (128 B)
 constexpr int BE_ACC = 16;            // floats per pixel of the fold accumulator (15 used)
 constexpr int BE_GREC = 12;           // floats per patch of the backward chain-rule record
 constexpr int BE_CREC = 16;           // floats per patch of the colour record of the TRAINFWD pass: C[9], M^-1[6] (packed 00,01,02,11,12,22)
-constexpr int BE_TW = 36;             // floats per pixel of the packed training-target record (be_train.cu)
+constexpr int BE_TW = 33;             // floats per pixel of the packed training targets: 8 float4 planes + 1 scalar plane (be_train.cu)
 
 enum BeRunMode { BE_RUN_COLORS = 0, BE_RUN_INFER = 1, BE_RUN_TRAINFWD = 2 };
 
@@ -54,7 +54,8 @@ struct BeLossArgs {
     const float* table;               // [N][BE_REC]
     const float* gtable;              // [N][BE_GREC]
     const float* crec;                // [N][BE_CREC] (global loss: written by the TRAINFWD pass)
-    const float* T;                   // [NB][H][W][BE_TW] packed targets (global loss)
+    const float* T;                   // packed targets of the global loss: 8 float4 planes + 1 scalar plane over [NB][H][W] (be_train.cu)
+    int same_gt;                      // img_gt is img_ny (the training call, global_training.py:210): the loss kernel never touches the GT planes
     const float *l_ny, *l_gt, *l_bd, *l_deri;   // local loss: [NB,R,R,3], [NB,R,R,3], [NB,R,R], [NB,R-2,R-2,3]
     float* grad;                      // [N][12|10] or nullptr
     float* partials;                  // [grid][8]

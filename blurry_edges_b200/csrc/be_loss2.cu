@@ -28,7 +28,11 @@ constexpr int NT = BE_THREADS;               // 224 render threads, 7 warps, two
 constexpr int NTHR = NT + 32;                // + helper warp
 constexpr int HALO = BE_MAX_R + 1;
 constexpr int NE = NT + 2 * HALO;
-constexpr size_t DYN_SMEM = sizeof(float4) * (9 * NE + BE_WARPS * 32 * 3 + BE_WARPS * 32 * 4 + 2 * NT);
+constexpr int NPLANE = 6;                    // stencil exchange planes: 2 (wedge weights) + 4 (projected Sobel gradients)
+#ifndef BE_LOSS2_PAD_SMEM
+#define BE_LOSS2_PAD_SMEM 0            // diagnosis only: extra dynamic shared memory, e.g. 65536 forces one CTA per SM
+#endif
+constexpr size_t DYN_SMEM = sizeof(float4) * (NPLANE * NE + BE_WARPS * 32 * 3 + BE_WARPS * 32 * 4 + 2 * NT) + BE_LOSS2_PAD_SMEM;
 
 template <int ID, int COUNT> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
 template <int ID, int COUNT> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
@@ -49,6 +53,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
     } while (!ok);
 }
 
+// Read-only loads the compiler may not merge with an earlier load of the same address: when img_gt is img_ny, stage D re-reads
+// the values stage A has already used instead of keeping them in registers across the two stencil stages.
+__device__ __forceinline__ float4 ldg_again4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_again2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     float a[8], b[4], c[2];
     bool hi_ = lane & 16;
@@ -66,7 +83,9 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
     return d;
 }
 
-template <int RCT>   // RCT = 21: patch size known at compile time (neighbour offsets become immediates), 0: generic
+// RCT = 21: patch size known at compile time (neighbour offsets become immediates), 0: generic.  SAMEGT: img_gt is img_ny (the
+// training call of the reference, global_training.py:210): the colour term reads the NY values and the GT values stay out of L1.
+template <int RCT, bool SAMEGT>
 __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     __shared__ __align__(16) float s_rec[2][BE_REC];
     __shared__ __align__(16) float s_grec[2][BE_GREC];
@@ -80,11 +99,13 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     // Pixels within HALO of the seam are written twice (as the low half of their own entry and as the high half of the entry NT
     // below); entries outside the patch stay zero.  Row wrap-around needs no mask: a wrapped neighbour is a border pixel, whose
     // Sobel gradients are zero, and only interior pixels (which never wrap) use the rendered-patch plane.
-    extern __shared__ float4 s_dyn[];             // 69 KB: above the 48 KB static limit
-    float4* const s_X = s_dyn;                    // [9][NE]
-    float4* const s_P2 = s_X;                     // [3][NE] (2 used) wedge weights of the rendered patch: (u1, u2) image 1, (u1, u2) image 2
-    float4* const s_G2 = s_X + 3 * NE;            // [6][NE] (4 used) projected Sobel gradients: PX (img 1), PX (img 2), PY (img 1), PY (img 2)
-    float4* const s_partA = s_X + 9 * NE;         // [7*32][3] per-lane A^T G partial sums (9 of 12 floats used), rows of 48 bytes
+    // 57 KB of dynamic shared memory (above the 48 KB static limit).  Two CTAs need a 132 KB carve-out, which leaves 124 KB of L1
+    // for the packed targets: one patch reads 441 x 144 B = 63 KB of them and shares 19 of its 21 columns with the next patch.
+    extern __shared__ float4 s_dyn[];
+    float4* const s_X = s_dyn;                    // [NPLANE][NE]
+    float4* const s_P2 = s_X;                     // [2][NE] wedge weights of the rendered patch: (u1, u2) image 1, (u1, u2) image 2
+    float4* const s_G2 = s_X + 2 * NE;            // [4][NE] projected Sobel gradients: PX (img 1), PX (img 2), PY (img 1), PY (img 2)
+    float4* const s_partA = s_X + NPLANE * NE;    // [7*32][3] per-lane A^T G partial sums (9 of 12 floats used), rows of 48 bytes
     float4* const s_partB = s_partA + BE_WARPS * 32 * 3;   // [7*32][4] per-lane backward sums (14 of 16 used), rows of 64 bytes, swizzled
     float4* const s_stash0 = s_partB + BE_WARPS * 32 * 4;  // [NT] thread-private (d1, d2) pairs, stage A -> D
     float4* const s_stash1 = s_stash0 + NT;                // [NT] thread-private (global boundary, bndry_dist) pairs
@@ -118,7 +139,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     if (tid < R) s_axis[tid] = be_axis(tid, R);
     if (tid < NFETCH) stash(0, tid, fetch(patch0, tid));
     if (tid == NTHR - 1) mbar_init(&s_vready, 1);
-    for (int i = tid; i < 9 * NE; i += NTHR) s_X[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < NPLANE * NE; i += NTHR) s_X[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     if (warp == BE_WARPS) {
@@ -291,8 +312,13 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float4 t2[2], t3[2], t4[2];                  // targets: issued before the arithmetic that hides their latency
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS + 2u)));
-                t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 2u * TPS)));
+                if (SAMEGT) {                            // gt = ny: values 0..5 (plane 0 and the first half of plane 1)
+                    t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
+                    t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
+                } else {                                 // values 6..11 (second half of plane 1 and plane 2)
+                    t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS + 2u)));
+                    t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 2u * TPS)));
+                }
                 t3[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 3u * TPS)));
                 t4[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 4u * TPS)));
             }
@@ -318,7 +344,8 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 float pv[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pv[c] = s ? hi(Pv[c]) : lo(Pv[c]);
-                const float gt[6] = {t1[s].x, t1[s].y, t2[s].x, t2[s].y, t2[s].z, t2[s].w};
+                const float gt[6] = {SAMEGT ? t2[s].x : t1[s].x, SAMEGT ? t2[s].y : t1[s].y, SAMEGT ? t2[s].z : t2[s].x,
+                                     SAMEGT ? t2[s].w : t2[s].y, SAMEGT ? t1[s].x : t2[s].z, SAMEGT ? t1[s].y : t2[s].w};
                 const float gi[6] = {t3[s].x, t3[s].y, t3[s].z, t3[s].w, t4[s].x, t4[s].y};
                 gb_[s] = t4[s].z; bd_[s] = t4[s].w;
                 float l0 = 0.0f, l1 = 0.0f;
@@ -344,9 +371,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float4 t6[2], t7[2], t8[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                t6[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 6u * TPS)));
-                t7[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 7u * TPS)));
-                t8[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 8u * TPS)));
+                t6[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 5u * TPS)));      // values 20..31: derivative targets
+                t7[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 6u * TPS)));
+                t8[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 7u * TPS)));
             }
             f2 ux[4], uy[4];                           // Sobel responses of (u1, u2) of image 1 and of image 2
 #pragma unroll
@@ -468,10 +495,10 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float zgv[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
-                const float2 q1 = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
+                const float4 q0 = SAMEGT ? ldg_again4(a.T + tp[s]) : __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
+                const float2 q1 = SAMEGT ? ldg_again2(a.T + (tp[s] + TPS)) : __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
                 ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
-                zgv[s] = __ldg(a.T + (tp[s] + 5u * TPS));
+                zgv[s] = __ldg(a.T + (8u * TPS + (tp[s] >> 2)));        // value 32: the scalar plane
             }
             const float4 sd = s_stash0[tid], sg = s_stash1[tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);
@@ -583,10 +610,17 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
 
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    static bool configured21[BE_MAX_DEVICES] = {}, configured0[BE_MAX_DEVICES] = {};
-    be_opt_in_smem(be_loss2_kernel<21>, DYN_SMEM, configured21);
-    be_opt_in_smem(be_loss2_kernel<0>, DYN_SMEM, configured0);
-    if (a.g.R == 21) be_loss2_kernel<21><<<grid, NTHR, DYN_SMEM, st>>>(a);
-    else be_loss2_kernel<0><<<grid, NTHR, DYN_SMEM, st>>>(a);
+    static bool configured[4][BE_MAX_DEVICES] = {};
+    be_opt_in_smem(be_loss2_kernel<21, false>, DYN_SMEM, configured[0]);
+    be_opt_in_smem(be_loss2_kernel<21, true>, DYN_SMEM, configured[1]);
+    be_opt_in_smem(be_loss2_kernel<0, false>, DYN_SMEM, configured[2]);
+    be_opt_in_smem(be_loss2_kernel<0, true>, DYN_SMEM, configured[3]);
+    if (a.g.R == 21) {
+        if (a.same_gt) be_loss2_kernel<21, true><<<grid, NTHR, DYN_SMEM, st>>>(a);
+        else be_loss2_kernel<21, false><<<grid, NTHR, DYN_SMEM, st>>>(a);
+    } else {
+        if (a.same_gt) be_loss2_kernel<0, true><<<grid, NTHR, DYN_SMEM, st>>>(a);
+        else be_loss2_kernel<0, false><<<grid, NTHR, DYN_SMEM, st>>>(a);
+    }
     ++g_be_launches;
 }

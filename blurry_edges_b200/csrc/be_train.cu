@@ -17,11 +17,16 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int T_NY = 0, T_GT = 6, T_GI = 12, T_GB = 18, T_BD = 19, T_ZG = 20, T_DGT = 24, T_DGI = 30;
+constexpr int T_NY = 0, T_GT = 6, T_GI = 12, T_GB = 18, T_BD = 19, T_DGT = 20, T_DGI = 26, T_ZG = 32;
 
-// T is stored as BE_TW/4 planes of float4 per pixel ([9][B*H*W] float4): the threads of a warp own neighbouring pixels, so a
-// 16-byte load of one plane touches ~half the sectors of a record-major layout, and every fetched sector is fully used.
-__device__ __forceinline__ size_t t_off(size_t plane_stride, size_t pix, int k) { return (size_t)(k >> 2) * plane_stride + pix * 4 + (k & 3); }
+// T is stored as 8 planes of float4 per pixel ([8][B*H*W] float4, values 0..31) followed by one scalar plane (value 32, z_gt):
+// the threads of a warp own neighbouring pixels, so a 16-byte load of one plane touches ~half the sectors of a record-major
+// layout and every fetched sector is fully used.  No padding: the loss kernel re-reads the 441-pixel window of every patch and
+// lives on the L1 hits of the 19 columns it shares with the previous patch; 33 floats per pixel are 58 KB per window (51 KB when
+// img_gt is img_ny and the GT values are never touched), two resident CTAs have 124 KB of L1.
+__device__ __forceinline__ size_t t_off(size_t plane_stride, size_t pix, int k) {
+    return (k < 32) ? (size_t)(k >> 2) * plane_stride + pix * 4 + (k & 3) : (size_t)8 * plane_stride + pix;
+}
 
 __device__ __forceinline__ int cover_1d(int y, int R, int s, int np) {
     const int hi = min(y / s, np - 1);
@@ -74,6 +79,7 @@ __global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, con
                                                             const float* __restrict__ img_gt, const float* __restrict__ bndry_dist,
                                                             const float* __restrict__ deri, const float* __restrict__ bndry_depth,
                                                             float* __restrict__ T) {
+    const bool same_gt = (img_gt == img_ny);          // the GT values are then never read (BeLossArgs::same_gt)
     const size_t HW = (size_t)g.H * g.W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * HW) return;
@@ -86,11 +92,10 @@ __global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, con
         for (int c = 0; c < 3; ++c) {
             const size_t o = (((size_t)b * 2 + m) * HW + p) * 3 + c;          // dataset-native [B,2,H,W,3]
             T[t_off(PS, idx, T_NY + 3 * m + c)] = img_ny[o];
-            T[t_off(PS, idx, T_GT + 3 * m + c)] = img_gt[o];
+            if (!same_gt) T[t_off(PS, idx, T_GT + 3 * m + c)] = img_gt[o];
         }
     T[t_off(PS, idx, T_BD)] = log2f(bndry_dist[idx] + 1.0f);                  // global_training.py:118
     T[t_off(PS, idx, T_ZG)] = bndry_depth[idx];
-    T[t_off(PS, idx, 21)] = T[t_off(PS, idx, 22)] = T[t_off(PS, idx, 23)] = 0.0f;
     const bool interior = (y >= 1 && y < g.H - 1 && x >= 1 && x < g.W - 1);
 #pragma unroll
     for (int mc = 0; mc < 6; ++mc) {

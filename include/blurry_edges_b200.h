@@ -119,7 +119,9 @@ int be_fold_normalise(be_ctx* ctx, const float* dev_acc, int32_t B, int32_t acc_
  *         global_bndry [B,1,H,W] (may be NULL; they are detached targets), mask count -> dev_mask_count (one int64).
  * stage2: the seven loss terms (unweighted, [7]) and loss = sum gamma_k term_k ([1]); if dev_grad != NULL also
  *         d loss / d raw [B,L,12], computed analytically per patch (every folded target is detached in the reference).
- *         global_patches = (global batch) * L; dev_mask_count may have been summed over ranks by the caller. */
+ *         global_patches = (global batch) * L; dev_mask_count may have been summed over ranks by the caller.
+ * dev_img_gt may be the SAME pointer as dev_img_ny (the training loop of the reference passes the clean image twice,
+ * global_training.py:210); stage 2 then runs a kernel variant that never reads the duplicate values (smaller L1 footprint). */
 int be_global_loss_stage1(be_ctx* ctx, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
                           const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
                           float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream);

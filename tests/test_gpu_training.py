@@ -90,6 +90,36 @@ def test_global_loss_stress_parameters_within_fp32_noise_floor():
     assert emax < max(5e-5, 2 * floor) and el2 < max(2e-5, 2 * floor2), (emax, el2, floor, floor2)
 
 
+@pytest.mark.parametrize('gname', list(GEOMS))
+def test_global_loss_training_call_passes_the_same_tensor_twice(gname):
+    """global_training.py:210 calls criteria(est, img_gt, img_gt, ...): the clean image is both the colour-solve input and the
+    colour target.  The library detects the shared tensor (same device pointer) and runs the kernel variant that never reads the
+    GT planes of the packed targets; the result must equal the oracle fed the same tensor twice, and the two-tensor path fed a copy."""
+    from blurry_edges_b200 import GlobalLossFused
+    g, raw, _, img_gt, bd, deri, zgt = gloss_inputs(gname, 'normal', F32)
+    gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 0.5]
+    crit = GlobalLossFused(_gargs(GEOMS[gname], 2), None, 'cuda:0')
+    _set_gammas(crit, gam)
+    est = raw.clone().cuda().requires_grad_(True)
+    gt_d = img_gt.cuda()
+    loss = crit(est, gt_d, gt_d, bd.cuda(), deri.cuda(), zgt.cuda())
+    loss.backward()
+    assert crit.ctx.last_same_gt is True
+    terms = crit.terms.cpu().numpy()
+    r64 = raw.to(F64).requires_grad_(True)
+    l64, t64, _ = O.global_loss(r64, img_gt.to(F64), img_gt.to(F64), bd.to(F64), deri.to(F64), zgt.to(F64), gam, g, CAM, return_terms=True)
+    (g64,) = torch.autograd.grad(l64, r64)
+    assert abs(loss.item() - l64.item()) <= 5e-6 * abs(l64.item())
+    np.testing.assert_allclose(terms, t64.detach().numpy(), rtol=5e-6)
+    emax, el2 = _grad_err(est.grad.cpu().numpy(), g64.numpy())
+    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)
+    # the general variant on a copy of the tensor: same numbers (the arithmetic is identical, only the loads differ)
+    loss2, grad2, terms2 = _run_global(crit, raw, img_gt, img_gt.clone(), bd, deri, zgt)
+    assert crit.ctx.last_same_gt is False
+    assert abs(loss2 - loss.item()) <= 1e-6 * abs(loss2)
+    assert relmax(grad2, est.grad.cpu().numpy()) < 1e-6
+
+
 def test_global_loss_no_grad_and_eval_mode():
     from blurry_edges_b200 import GlobalLossFused
     g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('tiny', 'normal', F32)

@@ -13,6 +13,7 @@ from blurry_edges_b200 import GlobalLossFused  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+same = len(sys.argv) > 3 and sys.argv[3] == 'same'      # the training call of the reference: criteria(est, img_gt, img_gt, ...)
 S, L = 147, 4096
 cam = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
 args = argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=cam,
@@ -24,6 +25,8 @@ crit.update_gamma()
 raw = synth.raw_global(B, L, seed=300).cuda().requires_grad_(True)
 img = synth.image_pairs(B, S, S, seed=301).cuda()
 gt, bd, deri, zg = [t.cuda() for t in synth.loss_targets(B, S, S, seed=302)]
+if same:
+    img = gt
 for _ in range(3):
     raw.grad = None
     crit(raw, img, gt, bd, deri, zg).backward()
@@ -33,4 +36,4 @@ for _ in range(steps):
     raw.grad = None
     crit(raw, img, gt, bd, deri, zg).backward()
 torch.cuda.synchronize()
-print(f'B={B}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step wall, {B * L * steps / (time.perf_counter() - t0) / 1e6:.1f} M patches/s')
+print(f'B={B}{" same-gt" if same else ""}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step wall, {B * L * steps / (time.perf_counter() - t0) / 1e6:.1f} M patches/s')
