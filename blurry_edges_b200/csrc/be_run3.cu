@@ -30,10 +30,9 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int NCOMP = BE_THREADS;            // 224 render threads (7 warps)
 constexpr int NTHR = NCOMP + 32;             // + solver warp
 
-template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
-template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHR) : "memory"); }
-__device__ __forceinline__ void sync_full(int p) { if (p == 0) bar_sync_id<1>(); else if (p == 1) bar_sync_id<2>(); else bar_sync_id<3>(); }
-__device__ __forceinline__ void arrive_full(int p) { if (p == 0) bar_arrive_id<1>(); else if (p == 1) bar_arrive_id<2>(); else bar_arrive_id<3>(); }
+// named barrier 1 + p (p = hand-off buffer): the barrier number is a register operand, no branch over three immediates
+__device__ __forceinline__ void sync_full(int p) { asm volatile("bar.sync %0, %1;" ::"r"(p + 1), "n"(NTHR) : "memory"); }
+__device__ __forceinline__ void arrive_full(int p) { asm volatile("bar.arrive %0, %1;" ::"r"(p + 1), "n"(NTHR) : "memory"); }
 constexpr int NBUF = 3;                       // hand-off buffers (stash, partial sums, colours, barriers): pipeline depth 2
 
 // DONE[parity] (colours published) is an mbarrier with one arrival (solver lane 0): a render warp waits for the solver only.
@@ -91,7 +90,7 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
     constexpr int NIMG = FOLD ? 2 : 1;
     constexpr int ACCW = INFER ? BE_ACC : 8;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // 64-byte aligned partial-sum rows: the store swizzle is an XOR on the address
     float4* s_pix = reinterpret_cast<float4*>(smem_raw + SM::off_pix);
     float4* s_st = reinterpret_cast<float4*>(smem_raw + SM::off_st);
     float* s_rec = reinterpret_cast<float*>(smem_raw + SM::off_rec);
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int l = gq + 8 * jj;
-                        const float4 v = pp[(wv * 32 + l) * 4 + ((qq + (l >> 1)) & 3)];
+                        const float4 v = pp[(wv * 32 + l) * 4 + (qq ^ ((l >> 1) & 3))];
                         t4.x += v.x; t4.y += v.y; t4.z += v.z; t4.w += v.w;
                     }
 #pragma unroll
@@ -222,19 +221,25 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
     }
     const f2 Y = mk2(s_axis[si[0]], s_axis[si[1]]);
     const float vm1 = valid[1] ? 1.0f : 0.0f;     // weight of the second slot in the normal-equation sums
+    const unsigned part_row0 = (smem_u32(s_part) + (unsigned)((warp * 32 + lane) * 64)) | (unsigned)(((lane >> 1) & 3) << 4);
 
     // (Re)load the pixel cache of slot s for the window of patch kpatch with 4-byte cp.async copies straight into the slot's
     // half of the (slot0, slot1) pairs: the warp does not wait for the pixels (they are first read in phase 1 of the next patch,
     // after cp_async_wait), so a warp whose column wraps no longer arrives late at the solver hand-off.
+    // image row of each slot (loop invariant): a reload then costs one 64-bit multiply-add for the column and one add per channel
+    const float* rowp[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) rowp[s] = a.img.p + ib * a.img.sb + (long long)(oy + y0 + si[s]) * a.img.sy + (long long)ox * a.img.sx;
     auto load_pixel = [&](int s, int kpatch) {
         const int x = (px0 + kpatch) * g.stride + j[s], y = y0 + si[s];
         const unsigned base = smem_u32(s_pix + tid) + 4u * s;
+        const float* src = rowp[s] + (long long)x * a.img.sx;
 #pragma unroll
         for (int m = 0; m < NIMG; ++m)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int q = 3 * m + c;
-                cp_async4(base + (q >> 1) * (NCOMP * 16) + (q & 1) * 8, a.img.p + ib * a.img.sb + m * a.img.sm + c * a.img.sc + (oy + y) * a.img.sy + (ox + x) * a.img.sx);
+                cp_async4(base + (q >> 1) * (NCOMP * 16) + (q & 1) * 8, src + m * a.img.sm + c * a.img.sc);
             }
         if (TRAIN) cp_async4(base + 3 * (NCOMP * 16), a.zgt + ((size_t)b * g.H + y) * g.W + x);
     };
@@ -319,11 +324,13 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
 #pragma unroll
                 for (int q = 0; q < 16; ++q) ssum[q] = 0.0f;
             }
-            {   // row of this lane, float4 columns rotated by (lane >> 1) so that the 16-byte stores of a quarter warp hit 8 bank groups
-                float4* row = s_part + ((size_t)(par * BE_WARPS + warp) * 32 + lane) * 4;
-                const int rot = lane >> 1;
+            {   // row of this lane (64 bytes), float4 column c stored at c ^ ((lane >> 1) & 3) so that the 16-byte stores of a quarter
+                // warp hit 8 bank groups; rows are 64-byte aligned, so the swizzle is one XOR on the shared-memory address
+                const unsigned row = part_row0 + (unsigned)par * (BE_WARPS * 32 * 64);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) row[(c + rot) & 3] = make_float4(ssum[4 * c], ssum[4 * c + 1], ssum[4 * c + 2], ssum[4 * c + 3]);
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row ^ (unsigned)(c << 4)), "f"(ssum[4 * c]), "f"(ssum[4 * c + 1]),
+                                 "f"(ssum[4 * c + 2]), "f"(ssum[4 * c + 3]) : "memory");
             }
             arrive_full(par);
 
