@@ -41,11 +41,11 @@ ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
 # the same with pixels sourced from the unfolded [2,3,R,R,Hp,Wp] tensor the reference signature hands in (SURVEY.md 8d "bytes_api")
 API_BYTES_PER_PATCH = 48.0 + 2 * 3 * R * R * 4 + 15 * S * S * 4 / L
 # dram__bytes_read.sum + dram__bytes_write.sum of be_run3_kernel<INFER> for one 64-pair launch, from the committed
-# `ncu --set full` capture profiles/r1i_run3_kernel_full.txt; None for other batch sizes
-TRAFFIC_NCU_64 = 155.289856e6 + 38.718976e6
+# `ncu --set full` capture profiles/r1y_run3_kernel_full.txt; None for other batch sizes
+TRAFFIC_NCU_64 = 155.284992e6 + 38.297600e6
 TRAFFIC_NCU = None
-# warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1i_run3_kernel_full.txt)
-WARP_INST_PER_PATCH = 3991.0
+# warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1y_run3_kernel_full.txt)
+WARP_INST_PER_PATCH = 3868.0
 SM_COUNT, SMSP_PER_SM = 148, 4
 
 
