@@ -97,3 +97,15 @@ def test_two_rank_recipes(worker):
     out = mgr.dict()
     mp.spawn(worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bench.py calls it on every rank of a multi-rank run; without NVML / on a single-node box it must do nothing and say so."""
+    import os
+    from blurry_edges_b200.dist_utils import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa_node(0)
+    assert info['device'] == 0 and isinstance(info['bound'], bool)
+    if not info['bound']:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
