@@ -21,6 +21,9 @@ GEOS = {
     'R7_s2': dict(R=7, stride=2, H=15, W=15, w=1.0),
     'R21_s5_w05': dict(R=21, stride=5, H=41, W=46, w=0.5),
     'R15_s4_w2': dict(R=15, stride=4, H=31, W=39, w=2.0),
+    # even patch sizes (no centre pixel, R*R even: the two pixel slots of the last thread are both in use or both empty)
+    'R12_s2_rect': dict(R=12, stride=2, H=22, W=26, w=1.0),
+    'R20_s3_rect': dict(R=20, stride=3, H=35, W=41, w=1.0),
     # runs of 1, 2 and 3 patches: the prologue / drain of the depth-2 pipeline and its three hand-off buffers
     'one_patch': dict(R=21, stride=2, H=21, W=21, w=1.0),
     'two_patches': dict(R=21, stride=2, H=21, W=23, w=1.0),
