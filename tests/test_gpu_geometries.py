@@ -97,3 +97,25 @@ def test_global_loss_other_geometries(name):
     emax = float(np.abs(got - ref).max() / np.abs(ref).max())
     el2 = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
     assert emax < 5e-5 and el2 < 2e-5, (emax, el2)
+
+
+def test_pixels_no_patch_covers_behave_as_in_the_reference():
+    """(H - R) not divisible by the stride leaves a border no patch covers: nn.Fold(ones) is 0 there, so the reference's averaged maps
+    are 0/0 = NaN and its depth (divided by max(count, 1)) is 0 (utils/postprocessing_loss.py:151-173).  Same pattern here, and the
+    covered pixels are unaffected."""
+    from blurry_edges_b200 import Context, _lib, make_config
+    g, cam = O.Geometry(R=21, stride=2, H=24, W=26, w=1.0), O.Camera(R=21)     # row 23 and column 25 are uncovered
+    est = O.restore_global(synth.raw_global(1, g.L, seed=55))
+    img = planar_pair(synth.image_pairs(1, g.H, g.W, seed=56))
+    ctx = Context(make_config(R=21, stride=2, H=24, W=26, w=1.0, max_batch=1), 'cuda:0')
+    out = ctx.render_fold(est.cuda(), img.cuda(), _lib.planar_layout(g.H, g.W))
+    ref = O.inference(est.to(F64), img.to(F64), g, cam, 10.39, None)
+    for n, r, o in zip(MAPS, ref, out):
+        o = o.cpu().double()
+        assert torch.equal(torch.isnan(o), torch.isnan(r)), n
+        ok = ~torch.isnan(r)
+        if n == 'depth':
+            assert float(o[..., 23, :].abs().max()) == 0.0 and float(o[..., :, 25].abs().max()) == 0.0
+        else:
+            assert bool(torch.isnan(r[..., 23, :]).all()) and bool(torch.isnan(r[..., :, 25]).all()), n
+        assert float((o[ok] - r[ok]).abs().max()) <= 2e-5 * float(r[ok].abs().max()), n
