@@ -299,8 +299,8 @@ def extra_configs(args, rank, world, dev, barrier):
     out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
                              'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2, 'ms_per_step_distinct_noisy_and_clean_images': ms_val,
                              'kernels_ncu': {'be_loss2_kernel': {'ms': 2.18, 'warp_inst_per_patch': 9539, 'issue_active': 0.50, 'l1_smem_pipe': 0.68},
-                                             'be_run3_kernel<TRAINFWD>': {'ms': 0.60, 'warp_inst_per_patch': 3273, 'issue_active': 0.65, 'l1_smem_pipe': 0.69},
-                                             'source': 'profiles/r1x_loss2_kernel_full.txt, profiles/r1k_train_kernels_full.txt'},
+                                             'be_run3_kernel<TRAINFWD>': {'ms': 0.57, 'warp_inst_per_patch': 3198, 'issue_active': 0.65, 'l1_smem_pipe': 0.72},
+                                             'source': 'profiles/r1y_train_kernels_full.txt'},
                              'algorithmic_bytes_per_patch': 810.0,
                              'hbm_frac_at_algorithmic_bytes': 810.0 * Bt2 * L / (ms / 1e3) / 1e9 / peaks()[0]}
     del crit2, raw2, img2, gt2, bd2, deri2, zg2
