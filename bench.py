@@ -333,6 +333,24 @@ def extra_configs(args, rank, world, dev, barrier):
     out['pass_a'] = {'metric': 'patches/sec pass A (ridge colours per single image), 128 images per GPU', 'value': 2 * Ba * L * world / (ms / 1e3),
                      'unit': 'single-image patches/s', 'ms_per_step': ms}
     del ctx_a, p10, img_a
+    # ---- local-stage training step (local_training.py:99-108: LocalLoss forward + backward, 64 patches per step in the reference) ----
+    from blurry_edges_b200 import LocalLossFused
+    Bl = 64
+    largs = ap.Namespace(batch_size=Bl, beta_bndry_loc=0.001, beta_smthns=0.0005, dynamic_epoch=200, **base)   # utils/args.py:34-36
+    lcrit = LocalLossFused(largs, dev)
+    lcrit.final_beta()
+    le, lny, lgt, lbd, lderi = [t.to(dev) for t in synth.local_batch(Bl, R, seed=350 + rank)]
+    le.requires_grad_(True)
+
+    def local_step():
+        le.grad = None
+        lcrit(le, lny, lgt, lbd, lderi).backward()
+
+    ms = _timed(local_step, max(steps, 10), 3, dev, barrier, world)
+    out['local_train_step'] = {'metric': 'patches/sec LocalLoss fwd+bwd (local_training.py: 64 single patches per step)', 'value': Bl * world / (ms / 1e3),
+                               'unit': 'single patches/s', 'ms_per_step': ms, 'patches_per_gpu': Bl,
+                               'note': 'launch bound: 3 kernels + autograd glue for 64 patches'}
+    del lcrit, le, lny, lgt, lbd, lderi
     # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
