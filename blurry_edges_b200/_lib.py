@@ -79,6 +79,8 @@ _SIGS = {
     'be_eval_depth': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
+    'be_global_loss_stage2_launch': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P]),
+    'be_global_loss_stage2_finish': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
     'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P]),
@@ -317,6 +319,28 @@ class Context:
         with torch.cuda.device(self.device):
             check(self.lib.be_global_loss_stage2(self.h, B, gam, int(global_patches), C.c_void_p(mask_count.data_ptr()),
                                                  _ptr(terms), _ptr(loss), _ptr(grad), _stream(self.device)))
+        return terms, loss, grad
+
+    def global_loss_stage2_launch(self, B, gammas, global_patches, want_grad=True):
+        """Start the loss kernel before the batch mask count is known (data-parallel: the count is being all-reduced).
+        -> (grad [B,L,12] | None, grad_depth [B,L,4] | None): hand both to global_loss_stage2_finish."""
+        kw = dict(device=self.device, dtype=torch.float32)
+        grad = torch.empty(B, self.L, 12, **kw) if want_grad else None
+        gdep = torch.empty(B, self.L, 4, **kw) if want_grad else None
+        gam = (C.c_double * 7)(*[float(x) for x in gammas])
+        with torch.cuda.device(self.device):
+            check(self.lib.be_global_loss_stage2_launch(self.h, B, gam, int(global_patches), _ptr(grad), _ptr(gdep), _stream(self.device)))
+        return grad, gdep
+
+    def global_loss_stage2_finish(self, B, gammas, global_patches, mask_count, grad, grad_depth):
+        """-> (terms [7], loss [1], grad): terms and loss from the kernel's partial sums and the (all-reduced) mask count; the depth
+        term's share of the gradient is normalised by the count and added to `grad` in place."""
+        kw = dict(device=self.device, dtype=torch.float32)
+        terms, loss = torch.empty(7, **kw), torch.empty(1, **kw)
+        gam = (C.c_double * 7)(*[float(x) for x in gammas])
+        with torch.cuda.device(self.device):
+            check(self.lib.be_global_loss_stage2_finish(self.h, B, gam, int(global_patches), C.c_void_p(mask_count.data_ptr()),
+                                                        _ptr(terms), _ptr(loss), _ptr(grad), _ptr(grad_depth), _stream(self.device)))
         return terms, loss, grad
 
     def local_loss(self, est, img_ny, img_gt, bndry_dist, deri, beta_bndry_loc, beta_smthns, want_grad=True):

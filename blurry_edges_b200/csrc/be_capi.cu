@@ -378,11 +378,18 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     return 0;
 }
 
-int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                          float* dev_terms, float* dev_loss, float* dev_grad, void* stream) {
+// Both halves of stage 2.  `launch`: the loss kernel; `finish`: the partial sums -> terms and loss (needs the mask count), and, when the
+// depth share of the gradient was kept apart (dev_grad_depth), its normalisation.  be_global_loss_stage2 = launch + finish with the
+// count already known; be_global_loss_stage2_launch / _finish let a data-parallel caller overlap the all-reduce of the count with
+// the loss kernel.
+static int loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                       float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, bool launch, bool finish, void* stream) {
     if (check_ctx(c)) return 1;
     if (B == 0) return 0;
-    BE_REQUIRE(gammas7 && dev_mask_count && dev_terms && dev_loss, "null pointer");
+    BE_REQUIRE(gammas7, "null pointer");
+    BE_REQUIRE(!finish || (dev_mask_count && dev_terms && dev_loss), "null pointer");
+    BE_REQUIRE(launch && finish ? true : (dev_grad == nullptr) == (dev_grad_depth == nullptr), "the split stage 2 needs dev_grad and dev_grad_depth together");
+    BE_REQUIRE(launch && finish ? dev_mask_count != nullptr : true, "null pointer");
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
     BE_REQUIRE(c->gtable, "be_global_loss_stage1 must run first");
     BE_REQUIRE(global_patches > 0, "global_patches must be positive");
@@ -393,6 +400,8 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     BeLossArgs a;
     memset(&a, 0, sizeof(a));
     a.table = c->table; a.gtable = c->gtable; a.crec = c->crec; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
+    a.grad_depth = (launch && finish) ? nullptr : dev_grad_depth;
+    a.defer_depth = (launch && !finish) ? 1 : 0;
     a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
     a.g = g; a.NB = B; a.same_gt = c->same_gt;
     pick_runs(g, B, LOSS_CTAS, LOSS_OVH, &a.G, &a.runs_per_row);
@@ -404,10 +413,29 @@ int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t g
     a.kc = (float)(gammas7[0] / norm[0]); a.kcc = (float)(gammas7[1] / norm[1]); a.kbc = (float)(gammas7[2] / norm[2]);
     a.ks = (float)(gammas7[3] / norm[3]); a.ksc = (float)(gammas7[4] / norm[4]); a.kbl = (float)(gammas7[5] / norm[5]);
     a.gamma_d = (float)gammas7[6];
-    be_launch_loss2(a, st);
-    be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
+    if (launch) be_launch_loss2(a, st);
+    if (finish) {
+        be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
+        if (!launch && dev_grad && dev_grad_depth)
+            be_launch_grad_depth_fixup(dev_grad, dev_grad_depth, a.mask_count, (size_t)B * g.Hp * g.Wp, st);
+    }
     BE_CUDA(cudaGetLastError());
     return 0;
+}
+
+int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                          float* dev_terms, float* dev_loss, float* dev_grad, void* stream) {
+    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, dev_terms, dev_loss, dev_grad, nullptr, true, true, stream);
+}
+
+int be_global_loss_stage2_launch(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, float* dev_grad,
+                                 float* dev_grad_depth, void* stream) {
+    return loss_stage2(c, B, gammas7, global_patches, nullptr, nullptr, nullptr, dev_grad, dev_grad_depth, true, false, stream);
+}
+
+int be_global_loss_stage2_finish(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                                 float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, void* stream) {
+    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, dev_terms, dev_loss, dev_grad, dev_grad_depth, false, true, stream);
 }
 
 int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,

@@ -58,6 +58,9 @@ struct BeLossArgs {
     int same_gt;                      // img_gt is img_ny (the training call, global_training.py:210): the loss kernel never touches the GT planes
     const float *l_ny, *l_gt, *l_bd, *l_deri;   // local loss: [NB,R,R,3], [NB,R,R,3], [NB,R,R], [NB,R-2,R-2,3]
     float* grad;                      // [N][12|10] or nullptr
+    float* grad_depth;                // [N][4] or nullptr: the depth term's share of the eta gradients, NOT divided by the mask count
+                                      // (deferred normaliser: the count of the whole batch is still being all-reduced)
+    int defer_depth;                  // 1: mask_count is not read by the loss kernel (it may be NULL / not final yet)
     float* partials;                  // [grid][8]
     const unsigned long long* mask_count;
     BeGeom g;
@@ -80,6 +83,7 @@ void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const flo
                           const float* bndry_depth, float* T, cudaStream_t st);
 void be_launch_loss(const BeLossArgs& a, cudaStream_t st);               // local-stage loss (be_train.cu)
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
+void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, size_t npatch, cudaStream_t st);
 void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
                            float* loss, cudaStream_t st);
 void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // renderer + fused fold (be_run3.cu)

@@ -521,7 +521,28 @@ __global__ void __launch_bounds__(256) be_loss_reduce_kernel(const float* __rest
     }
 }
 
+// deferred depth normaliser: grad[:, 8:12] += grad_depth / (mask count of the whole batch).  An empty mask leaves the gradient
+// alone (its depth share is exactly zero; the loss term itself is 0/0 = NaN as in the reference, global_training.py:127).
+__global__ void __launch_bounds__(256) be_grad_depth_fixup_kernel(float* __restrict__ grad, const float4* __restrict__ gd,
+                                                                   const unsigned long long* __restrict__ mask_count, size_t npatch) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npatch) return;
+    const unsigned long long cnt = *mask_count;
+    if (cnt == 0ull) return;
+    const float inv = 1.0f / (float)cnt;
+    const float4 d = gd[i];
+    float4* g = reinterpret_cast<float4*>(grad + i * 12) + 2;
+    float4 v = *g;
+    v.x = fmaf(d.x, inv, v.x); v.y = fmaf(d.y, inv, v.y); v.z = fmaf(d.z, inv, v.z); v.w = fmaf(d.w, inv, v.w);
+    *g = v;
+}
+
 }  // namespace
+
+void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, size_t npatch, cudaStream_t st) {
+    be_grad_depth_fixup_kernel<<<(unsigned)((npatch + 255) / 256), 256, 0, st>>>(grad, reinterpret_cast<const float4*>(grad_depth), mask_count, npatch);
+    ++g_be_launches;
+}
 
 void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st) {
     const size_t n = (size_t)B * g.H * g.W;

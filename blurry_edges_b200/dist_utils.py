@@ -7,15 +7,18 @@ import torch
 import torch.distributed as dist
 
 
-def sync_loss_normalisers(mask_count: torch.Tensor, local_patches: int, group=None):
+def sync_loss_normalisers(mask_count: torch.Tensor, local_patches: int, group=None, async_op: bool = False):
     """Depth-term mask count (global_training.py:127 divides by the count of the WHOLE batch) and patch count of the global
-    batch.  mask_count: int64[1] of this rank, summed in place over `group`.  Returns (mask_count, global_patches)."""
+    batch.  mask_count: int64[1] of this rank, summed in place over `group`.  Returns (mask_count, global_patches); with
+    async_op=True returns (mask_count, global_patches, work) where `work` is the pending all-reduce (None if there was nothing
+    to do): the caller overlaps it with the loss kernel and calls work.wait() before it uses the count."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
-        return mask_count, local_patches
+        return (mask_count, local_patches, None) if async_op else (mask_count, local_patches)
     world = dist.get_world_size(group)
+    work = None
     if world > 1:
-        dist.all_reduce(mask_count, op=dist.ReduceOp.SUM, group=group)
-    return mask_count, local_patches * world
+        work = dist.all_reduce(mask_count, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return (mask_count, local_patches * world, work if async_op else None) if async_op else (mask_count, local_patches * world)
 
 
 def reduce_accumulator(acc: torch.Tensor, group=None, dst_group_rank: int = 0):

@@ -99,10 +99,18 @@ class GlobalLossFused(nn.Module):
         want_grad = torch.is_grad_enabled() and est.requires_grad
         gimg, gbnd, cnt = self.ctx.global_loss_stage1(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self._f32(bndry_depth))
         npatch = B * L
+        work = None
         if self.process_group is not None:
             from .dist_utils import sync_loss_normalisers
-            cnt, npatch = sync_loss_normalisers(cnt, npatch, self.process_group)   # normalisers of the WHOLE batch
-        terms, loss, grad = self.ctx.global_loss_stage2(B, self.gammas(), npatch, cnt, want_grad)
+            cnt, npatch, work = sync_loss_normalisers(cnt, npatch, self.process_group, async_op=True)   # normalisers of the WHOLE batch
+        if work is None:
+            terms, loss, grad = self.ctx.global_loss_stage2(B, self.gammas(), npatch, cnt, want_grad)
+        else:
+            # the all-reduce of the 8-byte mask count runs on the collective's stream while the loss kernel runs on ours: only the
+            # final scalar combine and the depth term's share of the gradient wait for it
+            grad, gdep = self.ctx.global_loss_stage2_launch(B, self.gammas(), npatch, want_grad)
+            work.wait()
+            terms, loss, grad = self.ctx.global_loss_stage2_finish(B, self.gammas(), npatch, cnt, grad, gdep)
         self.global_image, self.global_bndry, self.terms, self.mask_count = gimg, gbnd, terms, cnt
         if want_grad:
             return _FusedLossFn.apply(est, loss, grad.to(est.dtype))

@@ -127,6 +127,15 @@ int be_global_loss_stage1(be_ctx* ctx, const float* dev_raw, const float* dev_im
                           float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream);
 int be_global_loss_stage2(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
                           float* dev_terms, float* dev_loss, float* dev_grad, void* stream);
+/* Stage 2 in two calls, for data-parallel callers: `launch` starts the loss kernel without the mask count (the depth term's share
+ * of the eta gradients goes, un-normalised, to dev_grad_depth [B,L,4]; dev_grad and dev_grad_depth are both NULL or both set), so
+ * the all-reduce of the count over the ranks overlaps the kernel; `finish`, ordered after the all-reduce, produces terms and loss
+ * and adds dev_grad_depth / count to dev_grad[:, :, 8:12].  launch + finish == be_global_loss_stage2 up to fp32 rounding of that
+ * last addition.  The same gammas7 / global_patches must be passed to both. */
+int be_global_loss_stage2_launch(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, float* dev_grad,
+                                 float* dev_grad_depth, void* stream);
+int be_global_loss_stage2_finish(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                                 float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, void* stream);
 
 /* LocalLoss.forward + backward (local_training.py:32-52): est [B,10] raw LocalStage output (angles wrapped inside),
  * img_ny / img_gt [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation,

@@ -160,6 +160,36 @@ def test_global_loss_batch_split_matches_full_batch():
     assert relmax(g_cat, grad) < 2e-6
 
 
+def test_global_loss_split_stage2_equals_fused_stage2():
+    """be_global_loss_stage2_launch / _finish (the loss kernel starts before the batch mask count is final, so a data-parallel
+    caller can overlap the all-reduce of the count with it) against be_global_loss_stage2 on the same inputs: same terms and loss,
+    gradients equal up to the rounding of grad += grad_depth / count; without gradients too; and with an empty mask (count 0)."""
+    from blurry_edges_b200 import GlobalLossFused
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('mid', 'normal', F32, B=2)
+    gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 0.5]
+    crit = GlobalLossFused(_gargs(GEOMS['mid'], 2), None, 'cuda:0')
+    dev = lambda t: t.cuda().contiguous()
+    for z in (zgt, torch.zeros_like(zgt)):
+        _, _, cnt = crit.ctx.global_loss_stage1(dev(raw), dev(img_ny), dev(img_gt), dev(bd), dev(deri), dev(z))
+        t0, l0, g0 = crit.ctx.global_loss_stage2(2, gam, 2 * g.L, cnt, True)
+        grad, gdep = crit.ctx.global_loss_stage2_launch(2, gam, 2 * g.L, True)
+        t1, l1, g1 = crit.ctx.global_loss_stage2_finish(2, gam, 2 * g.L, cnt, grad, gdep)
+        gn, gdn = crit.ctx.global_loss_stage2_launch(2, gam, 2 * g.L, False)
+        assert gn is None and gdn is None
+        t2, l2, _ = crit.ctx.global_loss_stage2_finish(2, gam, 2 * g.L, cnt, None, None)
+        torch.cuda.synchronize()
+        if int(cnt.item()) == 0:
+            assert torch.isnan(l0).all() and torch.isnan(l1).all() and torch.isnan(l2).all()          # 0/0, as the reference
+            assert torch.isfinite(g0).all() and torch.isfinite(g1).all() and float(gdep.abs().max()) == 0.0
+            np.testing.assert_array_equal(t1.cpu().numpy()[:6], t0.cpu().numpy()[:6])
+        else:
+            np.testing.assert_array_equal(t1.cpu().numpy(), t0.cpu().numpy())
+            np.testing.assert_array_equal(t2.cpu().numpy(), t0.cpu().numpy())
+            assert l1.item() == l0.item() == l2.item()
+            assert float(gdep.abs().max()) > 0.0
+        assert relmax(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-6
+
+
 def test_global_loss_full_size_one_pair_vs_oracle():
     """Config 3 geometry (147x147, 4096 patches): one pair against autograd through the fp64 oracle."""
     from blurry_edges_b200 import GlobalLossFused
