@@ -58,7 +58,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread (the timed region of
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 4 ms from a thread (the timed region of
     the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -107,7 +107,7 @@ class ClockSampler:
                 pass
             if last:
                 break
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nvml is not None:
@@ -143,7 +143,7 @@ class ClockSampler:
         if self.nvml is not None:
             sm = sorted(self.sm)
             return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
-                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 2 ms period, over the device-resident and the e2e timed regions'}
+                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 4 ms period, over the device-resident and the e2e timed regions'}
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
