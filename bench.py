@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the Blurry-Edges render -> fold -> depth hot path (BASELINE.json metric).
+"""Benchmark of the Blurry-Edges render -> fold -> depth hot path, forward + backward (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs B]
 
-A step = one pass B (blurry_edges_test.py:81-100: render both images with shared ridge colours, sharpened and
-refocused renders, boundary, depth mask/map, five folds) over one batch of synthetic 147x147 image pairs
-(config[1] of BASELINE.json: 64 pairs = 262144 patches per GPU).  N > 1 (torchrun, one rank per GPU): every rank
-processes its own batch of pairs (weak scaling, no data-path collective); time = max over ranks.
+A step = one global-stage training step of the hot path (global_training.py:208-211 without the transformer and the optimiser):
+GlobalLoss.forward (split_restore_params, render both images with shared ridge colours, boundary map, analytic depth, the two
+folds, the seven loss terms) + backward to the network output `est`, on one batch of basic-shape image pairs of the reference's
+own generator (BASELINE.json configs[2]; 32 pairs = 131072 patches per GPU).  The call is the reference's training call
+criteria(est, img_gt, img_gt, bndry_dist, deri, bndry_depth): the clean image is passed twice (global_training.py:210).
+N > 1 (torchrun, one rank per GPU): every rank holds its own 32 pairs of the global batch of 32 N (weak scaling); the only
+exchange is the 16-byte all-reduce of (depth-mask count, patch count) between the two kernel stages, inside the timed region.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same metric through the host-buffer
-C-ABI entry point with H2D/D2H copies inside the timed region, `roofline` the HBM roofline of the dominant kernel
-(be_run3_kernel, timed with CUDA events on its own stream), `cpu_baseline` the oracle port timed on this box's cores.
-`--impl reference` times the CPU port of the reference's eager PyTorch path (the reference itself is Python and is
-not present on the GPU box; oracle/be_oracle.py is pinned to it by tests/golden)."""
+Prints ONE JSON line (rank 0).  `value`: device-resident throughput through GlobalLossFused + backward; `e2e`: the same step
+through the host-buffer C-ABI entry point (be_host_global_loss: pinned host inputs -> H2D -> kernels -> D2H of loss + grad est),
+copies inside the timed region; `roofline`: HBM roofline of the dominant kernel (be_loss2_kernel, timed live with CUDA events on its
+stream); `cpu_baseline`: the CPU port of the reference's eager path (oracle/be_oracle.py + autograd) on this box's cores.
+`--impl reference` times that CPU port alone (the reference is Python source under /root/reference, absent on the GPU box; the
+port is pinned to it by tests/golden and was timed side by side with it)."""
 from __future__ import annotations
 
 import argparse
@@ -33,20 +37,19 @@ import torch  # noqa: E402
 S, R, STRIDE = 147, 21, 2
 HP = (S - R) // STRIDE + 1
 L = HP * HP
-METRIC = 'patches/sec render+fold+depth (BASELINE configs[1]: inference pass B; the fwd+bwd figures are under train_step*)'
+METRIC = 'patches/sec render+fold+depth fwd+bwd (GlobalLoss training step on est, BASELINE configs[2])'
 UNIT = 'patches/s'
-# algorithmic bytes per patch of pass B with pixels sourced from the image pair (SURVEY.md 8d / DESIGN.md 4):
-# params 48 + pixels 2*3*147^2*4/4096 = 126.6 + outputs 15 planes*147^2*4/4096 = 316.5
-ALGO_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
-# the same with pixels sourced from the unfolded [2,3,R,R,Hp,Wp] tensor the reference signature hands in (SURVEY.md 8d "bytes_api")
-API_BYTES_PER_PATCH = 48.0 + 2 * 3 * R * R * 4 + 15 * S * S * 4 / L
-# dram__bytes_read.sum + dram__bytes_write.sum of be_run3_kernel<INFER> for one 64-pair launch, from the committed
-# `ncu --set full` capture profiles/r1y_run3_kernel_full.txt; None for other batch sizes
-TRAFFIC_NCU_64 = 155.284992e6 + 38.297600e6
-TRAFFIC_NCU = None
-# warp-instructions per patch of be_run3_kernel<INFER> (smsp__inst_executed.sum / patches, profiles/r1y_run3_kernel_full.txt)
-WARP_INST_PER_PATCH = 3868.0
+# algorithmic bytes per patch of the training step, API-native layouts: est 48 + grad 48 + img_ny 126.6 + img_gt 126.6 +
+# bndry_dist 21.1 + deri 123.2 + bndry_depth 21.1 + folded global image / boundary written once and read once 2 x 147.7
+TRAIN_BYTES_PER_PATCH = 48 + 48 + 2 * (2 * 3 * S * S * 4 / L) + 2 * (S * S * 4 / L) + 2 * 3 * (S - 2) * (S - 2) * 4 / L + 2 * (7 * S * S * 4 / L)
+# inference pass B (configs[1]), pixels sourced from the image pair: params 48 + pixels 126.6 + 15 output planes 316.5
+INFER_BYTES_PER_PATCH = 48.0 + 2 * 3 * S * S * 4 / L + 15 * S * S * 4 / L
 SM_COUNT, SMSP_PER_SM = 148, 4
+CAM = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
+GAMMA_RANGES = dict(gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
+                    gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
+                    gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200])       # utils/args.py:53-61
+GAMMAS_IDX0 = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 1e-4]                                  # update_gamma() once (global_training.py:28-51)
 
 
 def peaks():
@@ -55,6 +58,16 @@ def peaks():
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     except Exception:
         return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_record(kernel):
+    """Per-launch figures of one `ncu --set full` capture, as committed under profiles/ by tools/ncu_record.py (never measured in
+    this run: the source file and its command travel with the numbers; None if the file is missing)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_records.json')) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -159,33 +172,44 @@ def restore_params(raw):
     return torch.cat([raw[..., :4] * 3, torch.remainder((raw[..., 4:8] + 1) * math.pi, 2 * math.pi), raw[..., 8:] + 0.5], dim=-1)
 
 
-def make_inputs(B, seed):
+def train_inputs(B, first, seed):
+    """One batch of the training step: raw network output est_raw = 0.1 * N(0,1)-like and basic-shape scenes
+    of the reference's generator (tests/golden/shapes147.npz, 8 scenes used round-robin; throughput does not depend on the values)."""
     import synth
-    est = restore_params(synth.raw_global(B, L, seed=seed)).contiguous()
-    img = synth.image_pairs(B, S, S, seed=seed + 1).permute(0, 1, 4, 2, 3).contiguous()   # planar [B,2,3,H,W]
-    return est, img
+    raw = synth.raw_global(B, L, seed=seed)
+    ny, gt, bd, deri, zg = synth.shapes_batch(B, first=first)
+    return raw, ny, gt, bd, deri, zg
 
 
-def cpu_reference_step(est, img, threads):
-    """The reference's eager fp32 CPU path for pass B, restated (oracle/be_oracle.py, trace-formula inverse as in
-    utils/postprocessing_loss.py:104-112); like the reference helper it handles one pair per call."""
+def loss_args(B):
+    return argparse.Namespace(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=CAM,
+                              batch_size=B, **GAMMA_RANGES)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's eager fp32 path for the training step, restated (oracle/be_oracle.py + autograd; trace-formula inverse
+# as in utils/postprocessing_loss.py:104-112)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_train_step(inp, threads):
     from oracle import be_oracle as O
+    raw, ny, gt, bd, deri, zg = inp
     g, cam = O.Geometry(H=S, W=S), O.Camera()
     torch.set_num_threads(threads)
-    with torch.no_grad():
-        for b in range(est.shape[0]):
-            O.inference(est[b:b + 1], img[b:b + 1], g, cam, 10.39, None, trace_form=True)
+    r = raw.clone().requires_grad_(True)
+    O.global_loss(r, gt, gt, bd, deri, zg, GAMMAS_IDX0, g, cam, trace_form=True).backward()     # the training call: clean image twice
+    return r.grad
 
 
-def time_cpu(pairs, reps, threads):
-    est, img = make_inputs(pairs, seed=900)
-    cpu_reference_step(est[:1], img[:1], threads)   # warm-up
-    best = float('inf')
+def time_cpu(pairs, warmup, reps, threads):
+    inp = train_inputs(pairs, 0, seed=900)
+    for _ in range(warmup):
+        cpu_train_step(inp, threads)
+    ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_reference_step(est, img, threads)
-        best = min(best, time.perf_counter() - t0)
-    return pairs * L / best, best
+        cpu_train_step(inp, threads)
+        ts.append(time.perf_counter() - t0)
+    return ts
 
 
 def run_reference(args, rank, world):
@@ -193,145 +217,194 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     pairs = args.ref_pairs
-    est, img = make_inputs(pairs, seed=900)
-    for _ in range(args.warmup):
-        cpu_reference_step(est[:1], img[:1], threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(est, img, threads)
-    dt = time.perf_counter() - t0
+    ts = time_cpu(pairs, args.warmup, args.steps, threads)
+    dt = sum(ts)
     val = args.steps * pairs * L / dt
     out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'pass B on {S}x{S} pairs, R={R}, stride={STRIDE}; each step = {pairs} pairs ({pairs * L} patches), '
-                                  'a bounded sample of the 64-pair batch'},
+           'config': {'workload': f'GlobalLoss forward + autograd backward to est on {S}x{S} basic-shape pairs, R={R}, stride={STRIDE}; each step = '
+                                  f'{pairs} pair(s) ({pairs * L} patches), a bounded sample of the 32-pair batch of BASELINE configs[2]'},
            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                            'sample': f'{pairs} pairs/step x {args.steps} steps, torch {torch.__version__} eager fp32 CPU, '
-                                      'oracle/be_oracle.py restatement of the reference (one pair per call, as the reference helper)'},
+                            'sample': f'{pairs} pair(s)/step x {args.steps} steps after {args.warmup} warm-up steps, torch {torch.__version__} eager fp32 '
+                                      'CPU + autograd, oracle/be_oracle.py restatement of the reference (timed within 3 % of the unmodified '
+                                      'reference in the build container)',
+                            'best_step_s': min(ts)},
            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    try:   # the fwd+bwd side of the metric: GlobalLoss forward + autograd backward of the same CPU port, one pair (bounded sample)
-        import synth
-        from oracle import be_oracle as O
-        g, cam = O.Geometry(H=S, W=S), O.Camera()
-        raw = synth.raw_global(1, L, seed=300).requires_grad_(True)
-        img_t = synth.image_pairs(1, S, S, seed=301)
-        gt, bd, deri, zg = synth.loss_targets(1, S, S, seed=302)
-        gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 1e-4]          # gamma_idx = 0 (global_training.py:28-51)
-        t0 = time.perf_counter()
-        O.global_loss(raw, img_t, gt, bd, deri, zg, gam, g, cam, trace_form=True).backward()
-        dt2 = time.perf_counter() - t0
-        out['train_step'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss, CPU port, autograd)', 'value': L / dt2, 'unit': UNIT,
-                             'sample': '1 pair, 1 repetition', 'seconds': dt2}
-    except Exception as e:
-        out['train_step'] = {'error': str(e)[:120]}
     _emit(out)
 
 
-def _timed(fn, steps, warmup, dev, barrier, world):
-    """ms per call of fn (CUDA events on the current stream, max over ranks)."""
+def _timed(fn, steps, warmup, dev, barrier, world, flush=None):
+    """ms per call of fn (CUDA events on the current stream, max over ranks); with `flush`, L2 is flushed (untimed) between calls."""
     import torch.distributed as dist
     for _ in range(warmup):
         fn()
     barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
-        fn()
-    b.record()
-    barrier()
-    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    if flush is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / steps
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
 
-def extra_configs(args, rank, world, dev, barrier):
-    """Secondary measurements of the other BASELINE.json configs (same JSON line, separate keys):
-    configs[2] global-loss training step fwd+bwd (4 pairs per GPU = batch 32 on 8 GPUs), configs[3] one 1027x1027 pair with
-    its 121 blocks sharded over the ranks, configs[4] densify 'w' with 32 pairs per GPU (256 on 8 GPUs)."""
+def parity_checks(rank, world, dev):
+    """N > 1 only: the sharded computations against the single-rank ones on the same global inputs (every rank can build all of
+    them; the inputs are functions of the global sample index)."""
+    import torch.distributed as dist
+    import synth
+    from blurry_edges_b200 import BigImageFused, GlobalLossFused, shard_blocks
+    out = {}
+    # ---- training: ranks hold uneven slices (rank r holds 1 + (r % 2) pairs) of one global batch ----
+    sizes = [1 + (r % 2) for r in range(world)]
+    lo = sum(sizes[:rank])
+    Bg = sum(sizes)
+    raw, ny, gt, bd, deri, zg = [t.to(dev) for t in train_inputs(Bg, 0, seed=700)]
+    full = GlobalLossFused(loss_args(Bg), None, dev)
+    full.update_gamma()
+    rf = raw.clone().requires_grad_(True)
+    lf = full(rf, gt, gt, bd, deri, zg)
+    lf.backward()
+    shard = GlobalLossFused(loss_args(sizes[rank]), None, dev, process_group=dist.group.WORLD, grad_reduce='sum')
+    shard.update_gamma()
+    sl = slice(lo, lo + sizes[rank])
+    rs = raw[sl].clone().requires_grad_(True)
+    ls = shard(rs, gt[sl], gt[sl], bd[sl], deri[sl], zg[sl])
+    ls.backward()
+    tot = ls.detach().clone()
+    dist.all_reduce(tot)
+    e = torch.stack([(tot - lf.detach()).abs() / lf.detach().abs(), (rs.grad - rf.grad[sl]).abs().max() / rf.grad.abs().max()]).double()
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    out['train'] = {'loss_rel_err_sum_of_shares_vs_single_rank': float(e[0]), 'grad_max_err_rel_to_max': float(e[1]),
+                    'pairs_per_rank': sizes, 'ok': bool(e[0] < 2e-6 and e[1] < 2e-6)}
+    del full, shard
+    # ---- big image: 323x323 (3x3 blocks) sharded over the ranks against all blocks on one rank ----
+    big = 323
+    bargs = argparse.Namespace(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=CAM,
+                               batch_size=1, big_img_size=[big, big], n_margin_patch=10, densify=None)
+    img = (torch.from_numpy(synth.photon_pairs(1, big, big, seed=63)).float() / 190.0).permute(0, 1, 4, 2, 3)[0].contiguous().to(dev)
+    est = torch.stack([restore_params(synth.raw_global(1, L, seed=170 + k))[0] for k in range(9)]).to(dev)
+    sh = BigImageFused(bargs, None, dev, process_group=dist.group.WORLD)
+    b0, b1 = shard_blocks(sh.nblk, rank, world)
+    maps = sh(est[b0:b1], img)
+    worst = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+        single = BigImageFused(bargs, None, dev)(est, img)
+        worst[0] = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(maps, single))
+    dist.broadcast(worst, 0)
+    out['big'] = {'maps_max_err_rel_to_max_sharded_vs_single_rank': float(worst), 'size': big, 'ok': bool(worst < 2e-6)}
+    return out
+
+
+def extra_configs(args, rank, world, dev, barrier, flush):
+    """Secondary measurements of the other BASELINE.json configs (same JSON line, separate keys)."""
     import argparse as ap
     import synth
     from blurry_edges_b200 import BigImageFused, Context, GlobalLossFused, PostProcessFused, _lib, make_config, shard_blocks
     import torch.distributed as dist
-    cam = {'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6}
-    base = dict(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=cam)
+    base = dict(R=R, stride=STRIDE, w=1.0, alpha_lambda=5e-3, img_size=[S, S], mag=4.0, rho_prime=10.39, cam_params=CAM)
     out = {}
     steps = max(3, args.steps // 2)
-    # ---- configs[2]: training step of the loss (forward + analytic backward), data parallel -------------------------
-    Bt = 4
-    targs = ap.Namespace(batch_size=Bt, gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
-                         gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
-                         gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200], **base)
-    crit = GlobalLossFused(targs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
-    crit.update_gamma()
-    raw = synth.raw_global(Bt, L, seed=300 + rank).to(dev).requires_grad_(True)
-    img = synth.image_pairs(Bt, S, S, seed=301 + rank).to(dev)
-    gt, bd, deri, zg = [t.to(dev) for t in synth.loss_targets(Bt, S, S, seed=302 + rank)]
+    pg = dist.group.WORLD if world > 1 else None
+    # ---- configs[2] exactly: a global batch of 32 pairs split over the ranks (strong scaling: 32 / N pairs per GPU) ----
+    if 32 % world == 0:
+        Bt = 32 // world
+        crit = GlobalLossFused(loss_args(Bt), None, dev, process_group=pg)
+        crit.update_gamma()
+        raw, ny, gt, bd, deri, zg = [t.to(dev) for t in train_inputs(Bt, rank * Bt, seed=300 + rank)]
+        raw.requires_grad_(True)
 
-    def train_step():                                   # the training call of the reference passes the clean image twice
-        raw.grad = None                                 # (global_training.py:210: criteria(est, img_gt, img_gt, ...))
-        crit(raw, gt, gt, bd, deri, zg).backward()
+        def strong_step():
+            raw.grad = None
+            crit(raw, gt, gt, bd, deri, zg).backward()
 
-    ms = _timed(train_step, steps, 3, dev, barrier, world)
-    out['train_step'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss, configs[2])', 'value': Bt * L * world / (ms / 1e3), 'unit': UNIT,
-                         'ms_per_step': ms, 'pairs_per_gpu': Bt, 'collective': '8-byte mask-count all-reduce between the two loss stages',
-                         'call': 'criteria(est, img_gt, img_gt, bndry_dist, deri, bndry_depth) + backward, as global_training.py:210-211'}
-    # the same step with the whole batch of configs[2] (32 pairs) on every GPU: throughput of the kernels once the GPU is full
-    Bt2 = 32
-    targs.batch_size = Bt2
-    crit2 = GlobalLossFused(targs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
-    crit2.update_gamma()
-    raw2 = synth.raw_global(Bt2, L, seed=330 + rank).to(dev).requires_grad_(True)
-    img2 = synth.image_pairs(Bt2, S, S, seed=331 + rank).to(dev)
-    gt2, bd2, deri2, zg2 = [t.to(dev) for t in synth.loss_targets(Bt2, S, S, seed=332 + rank)]
+        ms = _timed(strong_step, steps, 3, dev, barrier, world, flush)
+        out['train_step_batch32_total'] = {'metric': 'patches/sec fwd+bwd, global batch 32 split over the ranks (configs[2] as written)',
+                                           'value': 32 * L / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt, 'scaling': 'strong'}
+        # the validation call (global_training.py:166) has distinct noisy / clean images
+        def val_step():
+            raw.grad = None
+            crit(raw, ny, gt, bd, deri, zg).backward()
 
-    def train_step2():
-        raw2.grad = None
-        crit2(raw2, gt2, gt2, bd2, deri2, zg2).backward()
+        ms = _timed(val_step, steps, 3, dev, barrier, world, flush)
+        out['train_step_batch32_total']['ms_per_step_distinct_noisy_and_clean_images'] = ms
+        del crit, raw, ny, gt, bd, deri, zg
+    # ---- deterministic fold mode (torch.use_deterministic_algorithms, global_training.py:177): cost of the fixed-order fold ----
+    try:
+        Bd = 8
+        critd = GlobalLossFused(loss_args(Bd), None, dev, deterministic=True)
+        critd.update_gamma()
+        raw, ny, gt, bd, deri, zg = [t.to(dev) for t in train_inputs(Bd, 0, seed=360 + rank)]
+        raw.requires_grad_(True)
 
-    def val_step2():                                    # the validation call (global_training.py:166) has distinct noisy / clean images
-        raw2.grad = None
-        crit2(raw2, img2, gt2, bd2, deri2, zg2).backward()
+        def det_step():
+            raw.grad = None
+            critd(raw, gt, gt, bd, deri, zg).backward()
 
-    ms_val = _timed(val_step2, steps, 3, dev, barrier, world)
-    ms = _timed(train_step2, steps, 3, dev, barrier, world)
-    out['train_step_b32'] = {'metric': 'patches/sec loss fwd+bwd (GlobalLoss), 32 pairs per GPU', 'value': Bt2 * L * world / (ms / 1e3),
-                             'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bt2, 'ms_per_step_distinct_noisy_and_clean_images': ms_val,
-                             'kernels_ncu': {'be_loss2_kernel': {'ms': 2.18, 'warp_inst_per_patch': 9539, 'issue_active': 0.50, 'l1_smem_pipe': 0.68},
-                                             'be_run3_kernel<TRAINFWD>': {'ms': 0.57, 'warp_inst_per_patch': 3198, 'issue_active': 0.65, 'l1_smem_pipe': 0.72},
-                                             'source': 'profiles/r1y_train_kernels_full.txt'},
-                             'algorithmic_bytes_per_patch': 810.0,
-                             'hbm_frac_at_algorithmic_bytes': 810.0 * Bt2 * L / (ms / 1e3) / 1e9 / peaks()[0]}
-    del crit2, raw2, img2, gt2, bd2, deri2, zg2
-    # ---- SURVEY 8f #4: the Smish activation of LocalStage, an HBM-bound elementwise kernel (8 B/element fwd, 12 B/element bwd) ----
+        ms_d = _timed(det_step, steps, 3, dev, barrier, world, flush)
+        critd.deterministic = False
+        ms_n = _timed(det_step, steps, 3, dev, barrier, world, flush)
+        out['deterministic_fold'] = {'pairs_per_gpu': Bd, 'ms_per_step': ms_d, 'ms_per_step_atomic_fold': ms_n}
+        del critd, raw, ny, gt, bd, deri, zg
+    except TypeError:
+        pass
+    # ---- configs[1]: inference pass B on 64 pairs per GPU (blurry_edges_test.py:81-100), device-resident and through host buffers ----
+    Bi = 64
+    est_h = restore_params(synth.raw_global(Bi, L, seed=100 + rank)).contiguous().pin_memory()
+    img_h = synth.image_pairs(Bi, S, S, seed=101 + rank).permute(0, 1, 4, 2, 3).contiguous().pin_memory()
+    est, img = est_h.to(dev), img_h.to(dev)
+    ctx = Context(make_config(H=S, W=S, max_batch=Bi), dev)
+    layout = _lib.planar_layout(S, S)
+    o = ctx.alloc_outputs(Bi, True)
+    ctx.set_timing(True)
+    ms = _timed(lambda: ctx.render_fold(est, img, layout, out=o), steps, 3, dev, barrier, world, flush)
+    kt = ctx.last_timing()
+    ctx.set_timing(False)
+    host_out = ctx.host_render_fold(est_h, img_h, layout, want_thresholded=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.host_render_fold(est_h, img_h, layout, out=host_out)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hbm, _ = peaks()
+    out['inference_b64'] = {'metric': 'patches/sec inference pass B (configs[1]), 64 pairs per GPU', 'value': Bi * L * world / (ms / 1e3), 'unit': UNIT,
+                            'ms_per_step': ms, 'kernel_ms_be_run3': kt[2], 'e2e_value': Bi * L * world / (float(t.item()) / 1e3),
+                            'hbm_frac_of_kernel_at_algorithmic_bytes': INFER_BYTES_PER_PATCH * Bi * L / (kt[2] / 1e3) / 1e9 / hbm}
+    del ctx, est, img, est_h, img_h, o, host_out
+    # ---- SURVEY 8f #4: the Smish activation of LocalStage, an HBM-bound elementwise kernel (8 B/element fwd) ----
     from blurry_edges_b200 import smish
     xs = torch.rand(8192, 64, R, R, device=dev) * 8 - 4            # one LocalStage activation of 4096 patches x 2 images: 925 MB
-    gs = torch.rand_like(xs)
     ms_f = _timed(lambda: smish(xs), steps, 3, dev, barrier, world)
-    xg = xs.clone().requires_grad_(True)
-
-    def smish_fb():
-        xg.grad = None
-        smish(xg).backward(gs)
-
-    ms_fb = _timed(smish_fb, steps, 3, dev, barrier, world)
-    hbm, _ = peaks()
     nb = xs.numel() * 4
-    out['smish'] = {'metric': 'Smish activation (models/local_stage.py:4-6), fused elementwise kernel', 'elements': xs.numel(),
-                    'fwd_ms': ms_f, 'fwd_gbs': 2 * nb / (ms_f / 1e3) / 1e9, 'fwd_frac_of_hbm_peak': 2 * nb / (ms_f / 1e3) / 1e9 / hbm,
-                    'fwd_bwd_ms': ms_fb, 'bwd_gbs': 3 * nb / ((ms_fb - ms_f) / 1e3) / 1e9,
-                    'note': 'working set 1.85 GB >> L2; bwd figure = 3 arrays / (fwd+bwd - fwd) time, includes autograd glue'}
-    del xs, gs, xg
-    # ---- pass A (blurry_edges_test.py:125-128, colors_only=True): ridge colours of 2 x 64 single images, reported separately (8d) ----
+    out['smish'] = {'elements': xs.numel(), 'fwd_ms': ms_f, 'fwd_gbs': 2 * nb / (ms_f / 1e3) / 1e9, 'fwd_frac_of_hbm_peak': 2 * nb / (ms_f / 1e3) / 1e9 / hbm}
+    del xs
+    # ---- pass A (blurry_edges_test.py:125-128, colors_only=True): ridge colours of 2 x 64 single images ----
     Ba = 64
     ctx_a = Context(make_config(H=S, W=S, max_batch=Ba), dev)
     p10 = restore_params(synth.raw_global(2 * Ba, L, seed=340 + rank))[..., :10].contiguous().to(dev)
     img_a = synth.image_pairs(Ba, S, S, seed=341 + rank).permute(0, 1, 4, 2, 3).reshape(2 * Ba, 3, S, S).contiguous().to(dev)
     lay_a = _lib.single_planar_layout(S, S)
     ms = _timed(lambda: ctx_a.colors(p10, img_a, lay_a, _lib.PARAMS_LOCAL10), steps, 3, dev, barrier, world)
-    out['pass_a'] = {'metric': 'patches/sec pass A (ridge colours per single image), 128 images per GPU', 'value': 2 * Ba * L * world / (ms / 1e3),
-                     'unit': 'single-image patches/s', 'ms_per_step': ms}
+    out['pass_a'] = {'value': 2 * Ba * L * world / (ms / 1e3), 'unit': 'single-image patches/s', 'ms_per_step': ms}
     del ctx_a, p10, img_a
     # ---- local-stage training step (local_training.py:99-108: LocalLoss forward + backward, 64 patches per step in the reference) ----
     from blurry_edges_b200 import LocalLossFused
@@ -347,56 +420,50 @@ def extra_configs(args, rank, world, dev, barrier):
         lcrit(le, lny, lgt, lbd, lderi).backward()
 
     ms = _timed(local_step, max(steps, 10), 3, dev, barrier, world)
-    out['local_train_step'] = {'metric': 'patches/sec LocalLoss fwd+bwd (local_training.py: 64 single patches per step)', 'value': Bl * world / (ms / 1e3),
-                               'unit': 'single patches/s', 'ms_per_step': ms, 'patches_per_gpu': Bl,
-                               'note': 'launch bound: 3 kernels + autograd glue for 64 patches'}
+    out['local_train_step'] = {'value': Bl * world / (ms / 1e3), 'unit': 'single patches/s', 'ms_per_step': ms, 'patches_per_gpu': Bl}
     del lcrit, le, lny, lgt, lbd, lderi
-    # ---- configs[4]: densify 'w' ------------------------------------------------------------------------------------
+    # ---- configs[4]: densify 'w' ----
     Bw = 32
     pargs = ap.Namespace(batch_size=Bw, densify='w', **base)
     helper = PostProcessFused(pargs, None, dev, as_numpy=False)
     est_w = restore_params(synth.raw_global(Bw, L, seed=310 + rank)).to(dev)
     img_w = synth.image_pairs(Bw, S, S, seed=311 + rank).to(dev)
     ms = _timed(lambda: helper(est_w, img_w, colors_only=False), steps, 3, dev, barrier, world)
-    out['dense_w'] = {'metric': "patches/sec pass B, --densify 'w' (configs[4])", 'value': Bw * L * world / (ms / 1e3), 'unit': UNIT,
-                      'ms_per_step': ms, 'pairs_per_gpu': Bw}
-    # ---- configs[3]: one 1027x1027 pair, 121 blocks sharded over the ranks ------------------------------------------
+    out['dense_w'] = {'value': Bw * L * world / (ms / 1e3), 'unit': UNIT, 'ms_per_step': ms, 'pairs_per_gpu': Bw}
+    del helper, est_w, img_w
+    # ---- configs[3]: one 1027x1027 pair, 121 blocks sharded over the ranks ----
     big = 1027
     bargs = ap.Namespace(batch_size=1, big_img_size=[big, big], n_margin_patch=10, densify=None, **base)
-    bh = BigImageFused(bargs, None, dev, process_group=(dist.group.WORLD if world > 1 else None))
+    bh = BigImageFused(bargs, None, dev, process_group=pg)
     lo, hi = shard_blocks(bh.nblk, rank, world)
     est_b = restore_params(synth.raw_global(hi - lo, L, seed=320 + rank)).to(dev)
     big_img = (torch.from_numpy(synth.photon_pairs(1, big, big, seed=321)).float() / 190.0).permute(0, 1, 4, 2, 3)[0].contiguous().to(dev)
     ms = _timed(lambda: bh(est_b, big_img), steps, 3, dev, barrier, world)
     npatch_big = ((big - R) // STRIDE + 1) ** 2
-    out['big_1027'] = {'metric': 'patches/sec pass B + stitch + fold of one 1027x1027 pair (configs[3])', 'value': npatch_big / (ms / 1e3),
-                       'unit': UNIT, 'ms_per_image': ms, 'blocks': bh.nblk, 'blocks_this_rank': hi - lo, 'scaling': 'strong',
-                       'collective': 'sum-reduce of the [1027,1027,16] accumulator onto rank 0' if world > 1 else None}
+    out['big_1027'] = {'value': npatch_big / (ms / 1e3), 'unit': UNIT, 'ms_per_image': ms, 'blocks': bh.nblk, 'blocks_this_rank': hi - lo,
+                       'scaling': 'strong', 'collective': getattr(bh, 'collective', None) if world > 1 else None}
     return out
 
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from blurry_edges_b200 import Context, _lib, make_config
+    from blurry_edges_b200 import GlobalLossFused, _lib
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU port')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     B = args.pairs
-    # one rank per GPU on a multi-socket box: keep the rank (and, first-touch, its pinned buffers) on the GPU's NUMA node
     from blurry_edges_b200.dist_utils import bind_to_gpu_numa_node
     numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa) else {'bound': False}
-    global TRAFFIC_NCU
-    TRAFFIC_NCU = TRAFFIC_NCU_64 if B == 64 else None
-    est_h, img_h = make_inputs(B, seed=100 + rank)
-    est_h, img_h = est_h.pin_memory(), img_h.pin_memory()
-    est, img = est_h.to(dev), img_h.to(dev)
-    ctx = Context(make_config(H=S, W=S, max_batch=B), dev)
-    layout = _lib.planar_layout(S, S)
-    out = ctx.alloc_outputs(B, True)
-    # the six maps PostProcess.forward returns (blurry_edges_test.py:100); the script thresholds the depth on the host (:144)
-    host_out = ctx.host_render_fold(est_h, img_h, layout, want_thresholded=False)   # allocates pinned outputs + staging (untimed)
+    pg = dist.group.WORLD if world > 1 else None
+    host = [t.contiguous().pin_memory() for t in train_inputs(B, rank * B, seed=200 + rank)]
+    raw_h, ny_h, gt_h, bd_h, deri_h, zg_h = host
+    raw, gt, bd, deri, zg = [t.to(dev) for t in (raw_h, gt_h, bd_h, deri_h, zg_h)]
+    raw.requires_grad_(True)
+    crit = GlobalLossFused(loss_args(B), None, dev, process_group=pg)
+    crit.update_gamma()                                             # gamma_idx 0, as the first epoch of global_training.py:205
+    gammas = crit.gammas()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -404,10 +471,11 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def step():
-        ctx.render_fold(est, img, layout, out=out)
+    def step():                                                     # global_training.py:210-211 on est
+        raw.grad = None
+        crit(raw, gt, gt, bd, deri, zg).backward()
 
-    ctx.set_timing(True)
+    crit.ctx.set_timing(True)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -421,25 +489,31 @@ def run_ours(args, rank, world, local_rank):
             a.record()
             step()
             b.record()
-            kern.append(ctx.last_timing())                         # waits for this step's last kernel
+            kern.append(crit.ctx.last_train_timing())              # waits for this step's last kernel
         barrier()
         t_wall = time.perf_counter() - t_wall
         launches = _lib.launch_count() - n0
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-        ctx.set_timing(False)
+        crit.ctx.set_timing(False)
+        loss_val = float(crit.last_loss_share.item())
 
-        # end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H of the maps
+        # end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> kernels -> D2H of loss + grad est
         # (still inside the clock sampler: both timed regions are covered)
+        hout = crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, process_group=pg)
         for _ in range(max(1, args.warmup // 2)):
-            ctx.host_render_fold(est_h, img_h, layout, out=host_out)
+            crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, out=hout, process_group=pg)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.host_render_fold(est_h, img_h, layout, out=host_out)   # synchronises internally
+            crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, out=hout, process_group=pg)   # synchronises internally
         barrier()
         e2e_s = time.perf_counter() - t0
+    # the two paths must agree on the result
+    e2e_loss = float(hout[1].item())
+    e2e_grad_err = float((hout[2].to(dev) - raw.grad / (world if pg is not None else 1)).abs().max() / (raw.grad.abs().max() / (world if pg is not None else 1)))
 
-    extra = {} if args.no_extra else extra_configs(args, rank, world, dev, barrier)
+    parity = parity_checks(rank, world, dev) if world > 1 else None
+    extra = {} if args.no_extra else extra_configs(args, rank, world, dev, barrier, flush)
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -450,69 +524,70 @@ def run_ours(args, rank, world, local_rank):
     patches = B * L * world
     value = patches * args.steps / (dev_ms / 1e3)
     e2e = patches * args.steps / (e2e_ms / 1e3)
-    run_ms = sum(k[2] for k in kern) / len(kern)
-    shares = [sum(k[i] for k in kern) / len(kern) for i in range(4)]
+    names = ['memset', 'be_setup_kernel', 'be_run3_kernel<TRAINFWD>', 'be_train_normalise_kernel', 'be_train_pack_kernel', 'be_loss2_kernel',
+             'reduce+fixup']
+    shares = [sum(k[i] for k in kern) / len(kern) for i in range(7)]
+    loss2_ms = shares[5]
     peak, peak_src = peaks()
-    achieved = ALGO_BYTES_PER_PATCH * B * L / (run_ms / 1e3) / 1e9
+    achieved = TRAIN_BYTES_PER_PATCH * B * L / (loss2_ms / 1e3) / 1e9
+    rec = ncu_record('be_loss2_kernel') or {}
+    clocks = clk.summary()
+    h2d = int(sum(t.numel() for t in (raw_h, gt_h, bd_h, deri_h, zg_h)) * 4)
     res = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'inference pass B (render+fold+depth), {B} synthetic {S}x{S} pairs per GPU = {B * L} patches/step/GPU, '
-                                  f'R={R}, stride={STRIDE}, densify=None (BASELINE.json configs[1])',
-                      'l2': 'flushed between timed iterations (256 MiB write, untimed); working set 217 MB > 126 MB L2',
-                      'sharding': 'one batch per rank, no data-path collective'},
-           'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(B * (L * 12 + 6 * S * S) * 4),
-                   'd2h_bytes_per_step': int(B * 15 * S * S * 4), 'ms_per_step': e2e_ms / args.steps,
-                   'api': 'be_host_render_fold (pinned host buffers, synchronous): est + image pair in, the six maps of '
-                          'PostProcess.forward (15 planes, blurry_edges_test.py:100) out',
-                   'numa_binding_rank0': numa},
+           'config': {'workload': f'GlobalLoss training step fwd+bwd (BASELINE.json configs[2]): {B} basic-shape {S}x{S} pairs per GPU = {B * L} '
+                                  f'patches/step/GPU, R={R}, stride={STRIDE}, gamma_idx 0, est_raw = 0.1 N(0,1); scenes from the reference generator '
+                                  '(tests/golden/shapes147.npz, 8 scenes round-robin)',
+                      'call': 'criteria(est, img_gt, img_gt, bndry_dist, deri, bndry_depth) + backward (global_training.py:210-211)',
+                      'l2': 'flushed between timed iterations (256 MiB write, untimed)',
+                      'sharding': 'one 32-pair slice of the global batch per rank; 16-byte all-reduce of (mask count, patch count) inside the step'},
+           'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(B * L * 12 * 4 + 32),
+                   'ms_per_step': e2e_ms / args.steps,
+                   'api': 'be_host_global_loss[_begin/_end] (pinned host buffers, synchronous): est, clean image pair (passed twice, copied once), '
+                          'bndry_dist, deri, bndry_depth in; terms, loss and grad est out',
+                   'loss': e2e_loss, 'grad_max_err_vs_device_resident_path': e2e_grad_err, 'numa_binding_rank0': numa},
            'gpu_launches': int(launches),
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                        'traffic': TRAFFIC_NCU, 'kernel': 'be_run3_kernel<INFER>', 'kernel_ms': run_ms, 'peak_source': peak_src,
-                        'algorithmic_bytes_per_patch': ALGO_BYTES_PER_PATCH,
-                        'frac_if_pixels_came_unfolded': API_BYTES_PER_PATCH * B * L / (run_ms / 1e3) / 1e9 / peak,
-                        'note': 'the fused path is FP32/SFU-issue bound, not HBM bound (DESIGN.md section 4); '
-                                'see profiles/ for pipe utilisation'},
-           'sm_issue': {'note': 'binding resource of the fused kernel: warp-instruction issue slots (1 per SMSP per clock)',
-                        'warp_inst_per_patch_ncu': WARP_INST_PER_PATCH,
-                        'achieved_ginst_per_s': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / 1e9,
-                        'peak_ginst_per_s': SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) / 1e3,
-                        'frac': WARP_INST_PER_PATCH * B * L / (run_ms / 1e3) / (SM_COUNT * SMSP_PER_SM * (clk.summary()['sm_mhz'] or 1965) * 1e6)},
-           'kernel_ms': {'memset': shares[0], 'be_setup_kernel': shares[1], 'be_run3_kernel': shares[2], 'be_normalise_kernel': shares[3]},
-           'clocks': clk.summary(), 'wall_s_timed_region': t_wall}
+                        'traffic': rec.get('dram_bytes_per_launch') if B == rec.get('pairs') else None, 'traffic_source': rec.get('source'),
+                        'kernel': 'be_loss2_kernel', 'kernel_ms': loss2_ms, 'peak_source': peak_src,
+                        'algorithmic_bytes_per_patch': TRAIN_BYTES_PER_PATCH,
+                        'note': 'the fused step is bound by the SM (issue slots, L1/shared-memory data pipe), not by HBM: DESIGN.md section 3.2'},
+           'kernel_ms': dict(zip(names, shares)),
+           'kernel_share_of_step': {'be_loss2_kernel': loss2_ms / (dev_ms / args.steps), 'be_run3_kernel<TRAINFWD>': shares[2] / (dev_ms / args.steps)},
+           'loss_share_rank0': loss_val,
+           'clocks': clocks, 'wall_s_timed_region': t_wall}
+    if rec:
+        wi = rec.get('warp_inst_per_patch')
+        if wi:
+            peak_inst = SM_COUNT * SMSP_PER_SM * (clocks['sm_mhz'] or 1965) * 1e6
+            res['sm_issue'] = {'warp_inst_per_patch_ncu': wi, 'source': rec.get('source'),
+                               'frac_of_issue_slots_at_measured_kernel_time': wi * B * L / (loss2_ms / 1e3) / peak_inst}
+    if parity is not None:
+        res['parity_check'] = parity
     res.update(extra)
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, sec = time_cpu(args.ref_pairs, 2, cores)
-        res['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                               'sample': f'{args.ref_pairs} of the {B} pairs (best of 2, {sec:.2f} s), torch eager fp32 CPU port of the '
-                                         'reference (oracle/be_oracle.py), one pair per call'}
-        try:
-            from oracle import be_oracle as O, hostmath
-            g, cam = O.Geometry(H=S, W=S), O.Camera()
-            e2, i2 = make_inputs(8, seed=901)
-            hostmath.render_fold(e2[:1], i2[:1], g, cam)
-            t0 = time.perf_counter()
-            hostmath.render_fold(e2, i2, g, cam)
-            res['cpu_baseline']['c_port_openmp'] = {'value': 8 * L / (time.perf_counter() - t0), 'unit': UNIT,
-                                                    'note': 'oracle/be_hostmath.cpp: the kernels\' arithmetic on host cores, OpenMP over pairs'}
-        except Exception as e:  # the C port is optional evidence
-            res['cpu_baseline']['c_port_openmp'] = {'error': str(e)[:100]}
-        try:   # the reference's eager op chain on this same B200 (the oracle port on cuda:0, one pair per call)
+        ts = time_cpu(args.ref_pairs, 1, 3, cores)
+        res['cpu_baseline'] = {'value': args.ref_pairs * L / (sum(ts) / len(ts)), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                               'sample': f'{args.ref_pairs} of the {B} pairs per step, 1 warm-up + 3 timed steps ({sum(ts):.1f} s), torch eager fp32 CPU + '
+                                         'autograd port of the reference (oracle/be_oracle.py)', 'best_step_s': min(ts)}
+        try:   # the reference's eager op chain on this same B200 (the oracle port on cuda:0 with autograd)
             from oracle import be_oracle as O
             g, cam = O.Geometry(H=S, W=S), O.Camera()
-            e3, i3 = make_inputs(2, seed=902)
-            e3, i3 = e3.to(dev), i3.to(dev)
-            with torch.no_grad(), torch.device(dev):     # the oracle's constants (grids, ridge) are made on the default device
-                O.inference(e3[:1], i3[:1], g, cam, 10.39, None, trace_form=True)
+            inp = [t.to(dev) for t in train_inputs(1, 0, seed=902)]
+            with torch.device(dev):
+                def eager():
+                    r = inp[0].clone().requires_grad_(True)
+                    O.global_loss(r, inp[2], inp[2], inp[3], inp[4], inp[5], GAMMAS_IDX0, g, cam, trace_form=True).backward()
+                eager()
                 torch.cuda.synchronize(dev)
                 t0 = time.perf_counter()
-                for b in range(2):
-                    O.inference(e3[b:b + 1], i3[b:b + 1], g, cam, 10.39, None, trace_form=True)
+                for _ in range(3):
+                    eager()
                 torch.cuda.synchronize(dev)
-            res['cpu_baseline']['eager_port_on_this_gpu'] = {'value': 2 * L / (time.perf_counter() - t0), 'unit': UNIT,
-                                                             'note': 'the same torch restatement of the reference run eagerly on cuda:0 (fp32, '
-                                                                     'one pair per call): the launch/HBM-bound path the fused kernels replace'}
+            res['cpu_baseline']['eager_port_on_this_gpu'] = {'value': 3 * L / (time.perf_counter() - t0), 'unit': UNIT,
+                                                             'note': 'the same torch restatement + autograd run eagerly on cuda:0 (fp32, 1 pair per step)'}
         except Exception as e:
             res['cpu_baseline']['eager_port_on_this_gpu'] = {'error': str(e)[:100]}
     _emit(res)
@@ -541,10 +616,10 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--pairs', type=int, default=64, help='image pairs per GPU per step (BASELINE configs[1]: 64)')
-    ap.add_argument('--ref-pairs', type=int, default=8, help='pairs per step of the CPU reference sample')
+    ap.add_argument('--pairs', type=int, default=32, help='image pairs per GPU per step (BASELINE configs[2]: batch 32)')
+    ap.add_argument('--ref-pairs', type=int, default=1, help='pairs per step of the CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (train step, densify w, big image)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (inference, densify w, big image, ...)')
     ap.add_argument('--no-numa', action='store_true', help='multi-rank runs: do not bind each rank to the CPUs of its GPU\'s NUMA node')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -80,7 +80,11 @@ _SIGS = {
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_global_loss_stage2_launch': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P]),
-    'be_global_loss_stage2_finish': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P]),
+    'be_global_loss_stage2_finish': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    'be_host_global_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_double), _P, _P, _P]),
+    'be_host_global_loss_begin': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_double), C.c_int64, C.c_int32, _P, _P]),
+    'be_host_global_loss_end': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
+    'be_ctx_last_train_timing': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
     'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P]),
@@ -208,6 +212,14 @@ class Context:
             check(self.lib.be_ctx_last_timing(self.h, ms))
         return list(ms)
 
+    def last_train_timing(self):
+        """ms of (memset, setup, be_run3_kernel<TRAINFWD>, train normalise, train pack, be_loss2_kernel, reduce + depth fix-up) of
+        the last global-loss step (waits for it)."""
+        ms = (C.c_float * 7)()
+        with torch.cuda.device(self.device):
+            check(self.lib.be_ctx_last_train_timing(self.h, ms))
+        return list(ms)
+
     # ---- device-pointer entry points ---------------------------------------------------
     def cover_count(self):
         out = torch.empty(self.cfg.H, self.cfg.W, device=self.device, dtype=torch.float32)
@@ -296,11 +308,15 @@ class Context:
 
     # ---- training entry points -----------------------------------------------------------
     def global_loss_stage1(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, want_maps=True):
-        """-> (global_image [B,2,3,H,W] | None, global_bndry [B,1,H,W] | None, mask_count int64[1])"""
+        """-> (global_image [B,2,3,H,W] | None, global_bndry [B,1,H,W] | None, counts int64[2] = (mask count, B*L): the pair a
+        data-parallel caller all-reduces in one 16-byte collective)"""
         B, H, W, kw = raw.shape[0], self.cfg.H, self.cfg.W, dict(device=self.device, dtype=torch.float32)
         gimg = torch.empty(B, 2, 3, H, W, **kw) if want_maps else None
         gbnd = torch.empty(B, 1, H, W, **kw) if want_maps else None
-        cnt = torch.zeros(1, device=self.device, dtype=torch.int64)
+        tmpl = getattr(self, '_cnt_template', None)
+        if tmpl is None or tmpl[0] != B:
+            tmpl = self._cnt_template = (B, torch.tensor([0, B * self.L], dtype=torch.int64).to(self.device))
+        cnt = tmpl[1].clone()
         with torch.cuda.device(self.device):
             check(self.lib.be_global_loss_stage1(self.h, _ptr(raw), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri),
                                                  _ptr(bndry_depth), B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()),
@@ -332,14 +348,16 @@ class Context:
             check(self.lib.be_global_loss_stage2_launch(self.h, B, gam, int(global_patches), _ptr(grad), _ptr(gdep), _stream(self.device)))
         return grad, gdep
 
-    def global_loss_stage2_finish(self, B, gammas, global_patches, mask_count, grad, grad_depth):
-        """-> (terms [7], loss [1], grad): terms and loss from the kernel's partial sums and the (all-reduced) mask count; the depth
-        term's share of the gradient is normalised by the count and added to `grad` in place."""
+    def global_loss_stage2_finish(self, B, gammas, global_patches, counts, grad, grad_depth):
+        """-> (terms [7], loss [1], grad): terms and loss from the kernel's partial sums and the (all-reduced) counts int64[2] =
+        (mask count, true patch count of the global batch); the depth term's share of the gradient is normalised by the mask count
+        and added to `grad` in place; if the true patch count differs from `global_patches` (uneven shards) everything is rescaled."""
         kw = dict(device=self.device, dtype=torch.float32)
         terms, loss = torch.empty(7, **kw), torch.empty(1, **kw)
         gam = (C.c_double * 7)(*[float(x) for x in gammas])
+        true_p = C.c_void_p(counts.data_ptr() + 8) if counts.numel() > 1 else None
         with torch.cuda.device(self.device):
-            check(self.lib.be_global_loss_stage2_finish(self.h, B, gam, int(global_patches), C.c_void_p(mask_count.data_ptr()),
+            check(self.lib.be_global_loss_stage2_finish(self.h, B, gam, int(global_patches), C.c_void_p(counts.data_ptr()), true_p,
                                                         _ptr(terms), _ptr(loss), _ptr(grad), _ptr(grad_depth), _stream(self.device)))
         return terms, loss, grad
 
@@ -352,6 +370,42 @@ class Context:
             check(self.lib.be_local_loss(self.h, _ptr(est), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri), B,
                                          float(beta_bndry_loc), float(beta_smthns), _ptr(terms), _ptr(loss), _ptr(grad),
                                          _stream(self.device)))
+        return terms, loss, grad
+
+    def host_global_loss(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, gammas, want_grad=True, out=None, process_group=None):
+        """The training step on HOST tensors (CPU float32 contiguous, ideally pinned; dataset layouts of global_loss_stage1):
+        -> (terms [7], loss [1], grad [B,L,12] | None) as CPU tensors (`out` = the same triple, reused).  With a process_group the
+        mask count and the patch count of the global batch are all-reduced between the two halves of the call."""
+        B = raw.shape[0]
+        ts = (raw, img_ny, img_gt, bndry_dist, deri, bndry_depth)
+        for t in ts:
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise BlurryEdgesError('host_global_loss expects contiguous float32 CPU tensors')
+        if out is None:
+            pin = dict(dtype=torch.float32, pin_memory=True)
+            out = (torch.empty(7, **pin), torch.empty(1, **pin), torch.empty(B, self.L, 12, **pin) if want_grad else None)
+        terms, loss, grad = out
+        gam = (C.c_double * 7)(*[float(x) for x in gammas])
+        hp = [C.c_void_p(t.data_ptr()) for t in ts]
+        gp = C.c_void_p(grad.data_ptr()) if grad is not None else None
+        with torch.cuda.device(self.device):
+            if process_group is None:
+                check(self.lib.be_host_global_loss(self.h, *hp, B, gam, C.c_void_p(terms.data_ptr()), C.c_void_p(loss.data_ptr()), gp))
+            else:
+                import torch.distributed as dist
+                if getattr(self, '_host_cnt', None) is None:
+                    self._host_cnt = torch.zeros(2, device=self.device, dtype=torch.int64)
+                cnt = self._host_cnt
+                # the global patch count is only known after the all-reduce, but every rank needs it for its kernels' scales: the
+                # patch counts travel first (host-side, 8 bytes), the mask count between the two halves
+                npatch = torch.tensor([B * self.L], dtype=torch.int64, device=self.device)
+                dist.all_reduce(npatch, group=process_group)
+                npatch = int(npatch.item())
+                check(self.lib.be_host_global_loss_begin(self.h, *hp, B, gam, npatch, int(grad is not None), C.c_void_p(cnt.data_ptr()),
+                                                         _stream(self.device)))
+                dist.all_reduce(cnt[:1], group=process_group)
+                check(self.lib.be_host_global_loss_end(self.h, B, gam, npatch, C.c_void_p(cnt.data_ptr()), C.c_void_p(terms.data_ptr()),
+                                                       C.c_void_p(loss.data_ptr()), gp, _stream(self.device)))
         return terms, loss, grad
 
     # ---- host-buffer entry point (numpy / pinned host tensors in, numpy out) ------------

@@ -36,6 +36,7 @@ int fail(const char* fmt, ...) {
 }  // namespace
 
 constexpr int BE_HOST_CHUNKS = 16;  // maximum pipeline depth of the host-buffer entry point
+constexpr int BE_TRAIN_EVENTS = 10;
 
 struct be_ctx {
     be_config cfg;
@@ -65,7 +66,13 @@ struct be_ctx {
     float* T;           // [max_batch][H][W][BE_TW]
     float* partials;    // [max_batch*Hp*runs][8]
     int same_gt;        // the last be_global_loss_stage1 call had img_gt == img_ny
+    int train_B;        // pairs of the batch whose stage 1 ran last
+    int train_parts;    // rows of `partials` the last loss-kernel launch(es) wrote
     size_t train_bytes;
+    // staging of be_host_global_loss (lazily allocated)
+    float *ht_raw, *ht_ny, *ht_gt, *ht_bd, *ht_deri, *ht_zg, *ht_grad, *ht_gdep, *ht_scal;
+    int ht_want_grad;
+    cudaEvent_t tev[BE_TRAIN_EVENTS];   // per-kernel timing of the last training step (be_ctx_last_train_timing)
     // optional per-kernel timing of the last be_render_fold_fwd call (be_ctx_set_timing)
     int timing;
     cudaEvent_t ev[5];
@@ -214,6 +221,9 @@ int be_ctx_destroy(be_ctx* c) {
     cudaFree(c->table); cudaFree(c->acc);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
     cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec);
+    cudaFree(c->ht_raw); cudaFree(c->ht_ny); cudaFree(c->ht_gt); cudaFree(c->ht_bd); cudaFree(c->ht_deri); cudaFree(c->ht_zg);
+    cudaFree(c->ht_grad); cudaFree(c->ht_gdep); cudaFree(c->ht_scal);
+    for (int i = 0; i < BE_TRAIN_EVENTS; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
     if (c->blk_ev) cudaEventDestroy(c->blk_ev);
     for (int i = 0; i < 3; ++i) if (c->st_streams[i]) cudaStreamDestroy(c->st_streams[i]);
@@ -347,6 +357,45 @@ static int ensure_train_ws(be_ctx* c) {
     return 0;
 }
 
+static int ensure_train_events(be_ctx* c) {
+    if (c->tev[0]) return 0;
+    for (int i = 0; i < BE_TRAIN_EVENTS; ++i) BE_CUDA(cudaEventCreate(&c->tev[i]));
+    return 0;
+}
+
+// Stage 1 on pairs [b0, b0 + nb) of whole-batch device arrays holding Btot pairs: records, TRAINFWD render + fold, global maps,
+// packed targets.  The mask count is ADDED to *dev_mask_count (the caller zeroes it once per batch).  Disjoint ranges may be in
+// flight at the same time (every workspace array is indexed by pair).
+static int loss_stage1_range(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
+                             const float* dev_deri, const float* dev_bndry_depth, int b0, int nb, int Btot, float* dev_global_image,
+                             float* dev_global_bndry, int64_t* dev_mask_count, cudaStream_t st, bool tm) {
+    const BeGeom& g = c->g;
+    const int L = g.Hp * g.Wp;
+    const size_t HW = (size_t)g.H * g.W;
+    if (tm) cudaEventRecord(c->tev[0], st);
+    BE_CUDA(cudaMemsetAsync(c->acc + (size_t)b0 * HW * 8, 0, (size_t)nb * HW * 8 * sizeof(float), st));
+    if (tm) cudaEventRecord(c->tev[1], st);
+    be_launch_setup(dev_raw + (size_t)b0 * L * 12, BE_PARAMS_RAW12, nb * L, c->cam, c->table + (size_t)b0 * L * BE_REC,
+                    c->gtable + (size_t)b0 * L * BE_GREC, st);
+    if (tm) cudaEventRecord(c->tev[2], st);
+    BeRunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table + (size_t)b0 * L * BE_REC; a.acc = c->acc + (size_t)b0 * HW * 8;
+    a.img.p = dev_img_ny + (size_t)b0 * 6 * HW; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
+    a.zgt = dev_bndry_depth + (size_t)b0 * HW; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
+    a.crec = c->crec + (size_t)b0 * L * BE_CREC;
+    a.g = g; a.cam = c->cam; a.NB = nb; a.accH = g.H; a.accW = g.W;
+    pick_runs(g, nb, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+    launch_run(BE_RUN_TRAINFWD, a, st);
+    if (tm) cudaEventRecord(c->tev[3], st);
+    be_launch_train_normalise(c->acc, g, b0, nb, Btot, c->T, dev_global_image, dev_global_bndry, st);
+    if (tm) cudaEventRecord(c->tev[4], st);
+    be_launch_train_pack(g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
+    if (tm) cudaEventRecord(c->tev[5], st);
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
                           const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
                           float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream) {
@@ -355,26 +404,53 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     BE_REQUIRE(dev_raw && dev_img_ny && dev_img_gt && dev_bndry_dist && dev_deri && dev_bndry_depth && dev_mask_count, "null pointer");
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
     if (ensure_train_ws(c)) return 1;
+    if (c->timing && ensure_train_events(c)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const BeGeom& g = c->g;
-    const int L = g.Hp * g.Wp;
-    const size_t HW = (size_t)g.H * g.W;
-    BE_CUDA(cudaMemsetAsync(c->acc, 0, (size_t)B * HW * 8 * sizeof(float), st));
     BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), st));
-    be_launch_setup(dev_raw, BE_PARAMS_RAW12, B * L, c->cam, c->table, c->gtable, st);
-    BeRunArgs a;
-    memset(&a, 0, sizeof(a));
-    a.table = c->table; a.acc = c->acc;
-    a.img.p = dev_img_ny; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
-    a.zgt = dev_bndry_depth; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
-    a.crec = c->crec;
-    a.g = g; a.cam = c->cam; a.NB = B; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, B, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
-    launch_run(BE_RUN_TRAINFWD, a, st);
-    be_launch_train_normalise(c->acc, g, B, c->T, dev_global_image, dev_global_bndry, st);
-    be_launch_train_pack(g, B, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
     c->same_gt = (dev_img_gt == dev_img_ny);
-    BE_CUDA(cudaGetLastError());
+    c->train_B = B;
+    return loss_stage1_range(c, dev_raw, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, 0, B, B, dev_global_image,
+                             dev_global_bndry, dev_mask_count, st, c->timing != 0);
+}
+
+struct LossScales {
+    BeLossScale sc;
+    float kc, kcc, kbc, ks, ksc, kbl, gamma_d;
+};
+
+static LossScales loss_scales(const BeGeom& g, const double* gammas7, int64_t global_patches) {
+    LossScales o;
+    memset(&o, 0, sizeof(o));
+    const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)global_patches;
+    o.sc.nterms = 7;
+    const double norm[7] = {2 * RR * Np, 2 * RR * Np, RR * Np, 2 * Ri2 * Np, 2 * Ri2 * Np, RR * Np, 1.0};
+    for (int t = 0; t < 7; ++t) { o.sc.src[t] = t; o.sc.scale[t] = 1.0 / norm[t]; o.sc.gamma[t] = (float)gammas7[t]; o.sc.masked[t] = (t == 6); }
+    o.kc = (float)(gammas7[0] / norm[0]); o.kcc = (float)(gammas7[1] / norm[1]); o.kbc = (float)(gammas7[2] / norm[2]);
+    o.ks = (float)(gammas7[3] / norm[3]); o.ksc = (float)(gammas7[4] / norm[4]); o.kbl = (float)(gammas7[5] / norm[5]);
+    o.gamma_d = (float)gammas7[6];
+    return o;
+}
+
+// The loss kernel on pairs [b0, b0 + nb) of a batch of Btot pairs whose stage 1 has run.  dev_grad / dev_grad_depth are the arrays of
+// the whole batch; the CTAs' partial sums go to c->partials + part_off rows.  Returns the number of partial rows in *nparts.
+static int loss_kernel_range(be_ctx* c, int b0, int nb, int Btot, const LossScales& k, const int64_t* dev_mask_count, float* dev_grad,
+                             float* dev_grad_depth, bool defer, int part_off, int* nparts, cudaStream_t st) {
+    const BeGeom& g = c->g;
+    const size_t L = (size_t)g.Hp * g.Wp;
+    BeLossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = c->table + (size_t)b0 * L * BE_REC; a.gtable = c->gtable + (size_t)b0 * L * BE_GREC; a.crec = c->crec + (size_t)b0 * L * BE_CREC;
+    a.T = c->T; a.b0 = b0; a.NBT = Btot;
+    a.grad = dev_grad ? dev_grad + (size_t)b0 * L * 12 : nullptr;
+    a.grad_depth = (defer && dev_grad_depth) ? dev_grad_depth + (size_t)b0 * L * 4 : nullptr;
+    a.defer_depth = defer ? 1 : 0;
+    a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
+    a.g = g; a.NB = nb; a.same_gt = c->same_gt;
+    pick_runs(g, nb, LOSS_CTAS, LOSS_OVH, &a.G, &a.runs_per_row);
+    a.partials = c->partials + (size_t)part_off * 8;
+    a.kc = k.kc; a.kcc = k.kcc; a.kbc = k.kbc; a.ks = k.ks; a.ksc = k.ksc; a.kbl = k.kbl; a.gamma_d = k.gamma_d;
+    be_launch_loss2(a, st);
+    *nparts = nb * g.Hp * a.runs_per_row;
     return 0;
 }
 
@@ -383,7 +459,8 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
 // count already known; be_global_loss_stage2_launch / _finish let a data-parallel caller overlap the all-reduce of the count with
 // the loss kernel.
 static int loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                       float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, bool launch, bool finish, void* stream) {
+                       const int64_t* dev_true_patches, float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, bool launch,
+                       bool finish, void* stream) {
     if (check_ctx(c)) return 1;
     if (B == 0) return 0;
     BE_REQUIRE(gammas7, "null pointer");
@@ -391,33 +468,27 @@ static int loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t glob
     BE_REQUIRE(launch && finish ? true : (dev_grad == nullptr) == (dev_grad_depth == nullptr), "the split stage 2 needs dev_grad and dev_grad_depth together");
     BE_REQUIRE(launch && finish ? dev_mask_count != nullptr : true, "null pointer");
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
-    BE_REQUIRE(c->gtable, "be_global_loss_stage1 must run first");
+    BE_REQUIRE(c->gtable && c->train_B == B, "be_global_loss_stage1 must run first on the same batch (stage 1 saw %d pairs, stage 2 got %d)", c->train_B, B);
     BE_REQUIRE(global_patches > 0, "global_patches must be positive");
     BE_REQUIRE((double)B * c->g.H * c->g.W * BE_TW < 4.0e9, "batch of %d %dx%d pairs exceeds the 32-bit target offsets of the loss kernel", B, c->g.H, c->g.W);
     cudaStream_t st = (cudaStream_t)stream;
     const BeGeom& g = c->g;
-    const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)global_patches;
-    BeLossArgs a;
-    memset(&a, 0, sizeof(a));
-    a.table = c->table; a.gtable = c->gtable; a.crec = c->crec; a.T = c->T; a.grad = dev_grad; a.partials = c->partials;
-    a.grad_depth = (launch && finish) ? nullptr : dev_grad_depth;
-    a.defer_depth = (launch && !finish) ? 1 : 0;
-    a.mask_count = reinterpret_cast<const unsigned long long*>(dev_mask_count);
-    a.g = g; a.NB = B; a.same_gt = c->same_gt;
-    pick_runs(g, B, LOSS_CTAS, LOSS_OVH, &a.G, &a.runs_per_row);
-    BeLossScale sc;
-    memset(&sc, 0, sizeof(sc));
-    sc.nterms = 7;
-    const double norm[7] = {2 * RR * Np, 2 * RR * Np, RR * Np, 2 * Ri2 * Np, 2 * Ri2 * Np, RR * Np, 1.0};
-    for (int t = 0; t < 7; ++t) { sc.src[t] = t; sc.scale[t] = 1.0 / norm[t]; sc.gamma[t] = (float)gammas7[t]; sc.masked[t] = (t == 6); }
-    a.kc = (float)(gammas7[0] / norm[0]); a.kcc = (float)(gammas7[1] / norm[1]); a.kbc = (float)(gammas7[2] / norm[2]);
-    a.ks = (float)(gammas7[3] / norm[3]); a.ksc = (float)(gammas7[4] / norm[4]); a.kbl = (float)(gammas7[5] / norm[5]);
-    a.gamma_d = (float)gammas7[6];
-    if (launch) be_launch_loss2(a, st);
+    const LossScales k = loss_scales(g, gammas7, global_patches);
+    const bool tm = c->timing != 0 && c->tev[0];
+    if (launch) {
+        if (tm) cudaEventRecord(c->tev[6], st);
+        if (loss_kernel_range(c, 0, B, B, k, dev_mask_count, dev_grad, dev_grad_depth, !finish, 0, &c->train_parts, st)) return 1;
+        if (tm) cudaEventRecord(c->tev[7], st);
+    }
     if (finish) {
-        be_launch_loss_reduce(c->partials, B * g.Hp * a.runs_per_row, sc, a.mask_count, dev_terms, dev_loss, st);
+        if (tm) cudaEventRecord(c->tev[8], st);
+        const unsigned long long* tp = reinterpret_cast<const unsigned long long*>(dev_true_patches);
+        be_launch_loss_reduce(c->partials, c->train_parts, k.sc, reinterpret_cast<const unsigned long long*>(dev_mask_count), tp,
+                              (double)global_patches, dev_terms, dev_loss, st);
         if (!launch && dev_grad && dev_grad_depth)
-            be_launch_grad_depth_fixup(dev_grad, dev_grad_depth, a.mask_count, (size_t)B * g.Hp * g.Wp, st);
+            be_launch_grad_depth_fixup(dev_grad, dev_grad_depth, reinterpret_cast<const unsigned long long*>(dev_mask_count), tp,
+                                       (double)global_patches, (size_t)B * g.Hp * g.Wp, st);
+        if (tm) cudaEventRecord(c->tev[9], st);
     }
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -425,17 +496,137 @@ static int loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t glob
 
 int be_global_loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
                           float* dev_terms, float* dev_loss, float* dev_grad, void* stream) {
-    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, dev_terms, dev_loss, dev_grad, nullptr, true, true, stream);
+    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, nullptr, dev_terms, dev_loss, dev_grad, nullptr, true, true, stream);
 }
 
 int be_global_loss_stage2_launch(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, float* dev_grad,
                                  float* dev_grad_depth, void* stream) {
-    return loss_stage2(c, B, gammas7, global_patches, nullptr, nullptr, nullptr, dev_grad, dev_grad_depth, true, false, stream);
+    return loss_stage2(c, B, gammas7, global_patches, nullptr, nullptr, nullptr, nullptr, dev_grad, dev_grad_depth, true, false, stream);
 }
 
 int be_global_loss_stage2_finish(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                                 float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, void* stream) {
-    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, dev_terms, dev_loss, dev_grad, dev_grad_depth, false, true, stream);
+                                 const int64_t* dev_true_patches, float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth,
+                                 void* stream) {
+    return loss_stage2(c, B, gammas7, global_patches, dev_mask_count, dev_true_patches, dev_terms, dev_loss, dev_grad, dev_grad_depth, false, true,
+                       stream);
+}
+
+int be_ctx_last_train_timing(be_ctx* c, float* ms7) {
+    if (check_ctx(c)) return 1;
+    BE_REQUIRE(ms7 && c->timing && c->tev[0], "timing is not enabled (be_ctx_set_timing) or no training step has run since");
+    BE_CUDA(cudaEventSynchronize(c->tev[9]));
+    static const int from[7] = {0, 1, 2, 3, 4, 6, 8};
+    for (int i = 0; i < 7; ++i) BE_CUDA(cudaEventElapsedTime(&ms7[i], c->tev[from[i]], c->tev[from[i] + 1]));
+    return 0;
+}
+
+// ---- host-buffer form of the training step (the e2e path of bench.py; what a ctypes binding on the reference side calls with numpy
+// arrays).  begin: H2D in chunks of pairs on an internal copy stream, per chunk stage 1 and the loss kernel with the depth normaliser
+// deferred, on the CALLER's stream (so that a data-parallel caller can all-reduce the count stream-ordered after it);
+// end: reduce, depth fix-up, D2H of terms / loss / grad, synchronise. ----
+static int ensure_train_staging(be_ctx* c) {
+    if (c->ht_raw) return 0;
+    const BeGeom& g = c->g;
+    const size_t mb = (size_t)c->cfg.max_batch, HW = (size_t)g.H * g.W, L = (size_t)g.Hp * g.Wp, f = sizeof(float);
+    const size_t dHW = (size_t)(g.H - 2) * (g.W - 2);
+    BE_CUDA(cudaMalloc(&c->ht_raw, mb * L * 12 * f));
+    BE_CUDA(cudaMalloc(&c->ht_ny, mb * 6 * HW * f));
+    BE_CUDA(cudaMalloc(&c->ht_gt, mb * 6 * HW * f));
+    BE_CUDA(cudaMalloc(&c->ht_bd, mb * HW * f));
+    BE_CUDA(cudaMalloc(&c->ht_deri, mb * 6 * dHW * f));
+    BE_CUDA(cudaMalloc(&c->ht_zg, mb * HW * f));
+    BE_CUDA(cudaMalloc(&c->ht_grad, mb * L * 12 * f));
+    BE_CUDA(cudaMalloc(&c->ht_gdep, mb * L * 4 * f));
+    BE_CUDA(cudaMalloc(&c->ht_scal, 8 * f + sizeof(int64_t) * 2));
+    c->st_bytes += mb * (L * 28 + 14 * HW + 6 * dHW) * f + 48;
+    if (!c->st_streams[0])
+        for (int i = 0; i < 3; ++i) BE_CUDA(cudaStreamCreateWithFlags(&c->st_streams[i], cudaStreamNonBlocking));
+    if (!c->st_events[0])
+        for (int i = 0; i < 2 * BE_HOST_CHUNKS; ++i) BE_CUDA(cudaEventCreateWithFlags(&c->st_events[i], cudaEventDisableTiming));
+    return 0;
+}
+
+int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                              const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, int64_t global_patches,
+                              int32_t want_grad, int64_t* dev_mask_count, void* stream) {
+    if (check_ctx(c)) return 1;
+    BE_REQUIRE(raw && img_ny && img_gt && bndry_dist && deri && bndry_depth && gammas7 && dev_mask_count, "null pointer");
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d must be in [1, max_batch=%d]", B, c->cfg.max_batch);
+    BE_REQUIRE(global_patches > 0, "global_patches must be positive");
+    BE_REQUIRE((double)B * c->g.H * c->g.W * BE_TW < 4.0e9, "batch of %d %dx%d pairs exceeds the 32-bit target offsets of the loss kernel", B, c->g.H, c->g.W);
+    if (ensure_train_ws(c) || ensure_train_staging(c)) return 1;
+    const BeGeom& g = c->g;
+    const size_t HW = (size_t)g.H * g.W, L = (size_t)g.Hp * g.Wp, f = sizeof(float), dHW = (size_t)(g.H - 2) * (g.W - 2);
+    cudaStream_t s_k = (cudaStream_t)stream, s_in = c->st_streams[0];
+    const bool same = (img_gt == img_ny);
+    c->same_gt = same;
+    c->train_B = B;
+    const float* d_gt = same ? c->ht_ny : c->ht_gt;
+    const LossScales k = loss_scales(g, gammas7, global_patches);
+    // the copy stream must not overtake the previous call's kernels, which may still read the staging buffers
+    BE_CUDA(cudaEventRecord(c->st_events[2 * BE_HOST_CHUNKS - 1], s_k));
+    BE_CUDA(cudaStreamWaitEvent(s_in, c->st_events[2 * BE_HOST_CHUNKS - 1], 0));
+    BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), s_k));
+    static const int want = [] { const char* e = getenv("BE_HOST_TRAIN_CHUNKS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > BE_HOST_CHUNKS - 1 ? BE_HOST_CHUNKS - 1 : v); }();
+    const int nchunk = B < want ? B : want;
+    int part_off = 0;
+    for (int i = 0; i < nchunk; ++i) {
+        const int b0 = (int)((long long)B * i / nchunk), b1 = (int)((long long)B * (i + 1) / nchunk), nb = b1 - b0;
+        if (nb == 0) continue;
+        BE_CUDA(cudaMemcpyAsync(c->ht_raw + b0 * L * 12, raw + b0 * L * 12, nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_ny + b0 * 6 * HW, img_ny + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
+        if (!same) BE_CUDA(cudaMemcpyAsync(c->ht_gt + b0 * 6 * HW, img_gt + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_bd + b0 * HW, bndry_dist + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_deri + b0 * 6 * dHW, deri + b0 * 6 * dHW, nb * 6 * dHW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_zg + b0 * HW, bndry_depth + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaEventRecord(c->st_events[i], s_in));
+        BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[i], 0));
+        if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, dev_mask_count, s_k, false))
+            return 1;
+        int np_ = 0;
+        if (loss_kernel_range(c, b0, nb, B, k, nullptr, want_grad ? c->ht_grad : nullptr, want_grad ? c->ht_gdep : nullptr, true, part_off, &np_, s_k))
+            return 1;
+        part_off += np_;
+    }
+    c->train_parts = part_off;
+    c->ht_want_grad = want_grad;
+    BE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int be_host_global_loss_end(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                            float* terms7, float* loss1, float* grad, void* stream) {
+    if (check_ctx(c)) return 1;
+    BE_REQUIRE(gammas7 && dev_mask_count && terms7 && loss1, "null pointer");
+    BE_REQUIRE(c->ht_raw && c->train_B == B && B > 0, "be_host_global_loss_begin must run first on the same batch");
+    BE_REQUIRE(!grad || c->ht_want_grad, "be_host_global_loss_begin ran with want_grad = 0");
+    const BeGeom& g = c->g;
+    const size_t L = (size_t)g.Hp * g.Wp;
+    cudaStream_t s_k = (cudaStream_t)stream;
+    const LossScales k = loss_scales(g, gammas7, global_patches);
+    float* d_terms = c->ht_scal;
+    be_launch_loss_reduce(c->partials, c->train_parts, k.sc, reinterpret_cast<const unsigned long long*>(dev_mask_count), nullptr, 0.0, d_terms,
+                          d_terms + 7, s_k);
+    BE_CUDA(cudaMemcpyAsync(terms7, d_terms, 7 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    BE_CUDA(cudaMemcpyAsync(loss1, d_terms + 7, sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    if (grad) {
+        be_launch_grad_depth_fixup(c->ht_grad, c->ht_gdep, reinterpret_cast<const unsigned long long*>(dev_mask_count), nullptr, 0.0, (size_t)B * L, s_k);
+        BE_CUDA(cudaMemcpyAsync(grad, c->ht_grad, (size_t)B * L * 12 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    }
+    BE_CUDA(cudaGetLastError());
+    BE_CUDA(cudaStreamSynchronize(s_k));
+    return 0;
+}
+
+int be_host_global_loss(be_ctx* c, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
+                        const float* bndry_depth, int32_t B, const double* gammas7, float* terms7, float* loss1, float* grad) {
+    if (check_ctx(c)) return 1;
+    if (B == 0) return 0;
+    if (ensure_train_ws(c) || ensure_train_staging(c)) return 1;
+    int64_t* cnt = reinterpret_cast<int64_t*>(c->ht_scal + 8);
+    const int64_t np_ = (int64_t)B * c->g.Hp * c->g.Wp;
+    if (be_host_global_loss_begin(c, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, B, gammas7, np_, grad != nullptr, cnt, c->st_streams[1])) return 1;
+    return be_host_global_loss_end(c, B, gammas7, np_, cnt, terms7, loss1, grad, c->st_streams[1]);
 }
 
 int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
@@ -464,7 +655,7 @@ int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, cons
     sc.gamma[0] = 1.0f; sc.gamma[1] = (float)beta_bndry_loc; sc.gamma[2] = (float)beta_smthns;
     a.kc = (float)sc.scale[0]; a.kbl = (float)(beta_bndry_loc * sc.scale[1]); a.ks = (float)(beta_smthns * sc.scale[2]);
     be_launch_loss(a, st);
-    be_launch_loss_reduce(c->partials, B, sc, nullptr, dev_terms, dev_loss, st);
+    be_launch_loss_reduce(c->partials, B, sc, nullptr, nullptr, 0.0, dev_terms, dev_loss, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -715,17 +906,20 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
     if (B == 0) return 0;
     BE_REQUIRE(est && img && image && sharp && refoc && bndry && depth && conf, "null pointer");
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
+    BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_host_render_fold takes 12-parameter patches");
     BE_REQUIRE(layout->sb == 6LL * c->g.H * c->g.W, "host entry point needs pairs stored contiguously (layout.sb = 6*H*W)");
     const BeGeom& g = c->g;
     const size_t HW = (size_t)g.H * g.W, L = (size_t)g.Hp * g.Wp;
     const size_t mb = (size_t)c->cfg.max_batch;
     if (!c->st_est) {
-        for (int i = 0; i < 3; ++i) BE_CUDA(cudaStreamCreateWithFlags(&c->st_streams[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 2 * BE_HOST_CHUNKS; ++i) BE_CUDA(cudaEventCreateWithFlags(&c->st_events[i], cudaEventDisableTiming));
+        if (!c->st_streams[0])
+            for (int i = 0; i < 3; ++i) BE_CUDA(cudaStreamCreateWithFlags(&c->st_streams[i], cudaStreamNonBlocking));
+        if (!c->st_events[0])
+            for (int i = 0; i < 2 * BE_HOST_CHUNKS; ++i) BE_CUDA(cudaEventCreateWithFlags(&c->st_events[i], cudaEventDisableTiming));
         BE_CUDA(cudaMalloc(&c->st_est, mb * L * 12 * sizeof(float)));
         BE_CUDA(cudaMalloc(&c->st_img, mb * 6 * HW * sizeof(float)));
         BE_CUDA(cudaMalloc(&c->st_out, mb * 16 * HW * sizeof(float)));
-        c->st_bytes = mb * (L * 12 + 22 * HW) * sizeof(float);
+        c->st_bytes += mb * (L * 12 + 22 * HW) * sizeof(float);
     }
     // Software pipeline over chunks of pairs: H2D(chunk i+1) | kernels(chunk i) | D2H(chunk i-1) on three streams, so that the
     // PCIe transfers hide behind the renderer.  Measured on the B200 box (tools/microbench/pcie.py, BE_HOST_TRACE=1): the call is
@@ -747,7 +941,7 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
             const char* e = getenv("BE_HOST_WGT");
             if (e) {
                 int k = 0;
-                while (*e && k < BE_HOST_CHUNKS) { wgt[k++] = atoi(e); while (*e && *e != ',') ++e; if (*e == ',') ++e; }
+                while (*e && k < BE_HOST_CHUNKS) { const int v = atoi(e); wgt[k++] = v < 1 ? 1 : v; while (*e && *e != ',') ++e; if (*e == ',') ++e; }
                 if (k > 0) nw = k;
             }
             return true;
@@ -774,6 +968,7 @@ int be_host_render_fold(be_ctx* c, const float* est, int32_t param_mode, const f
     if (trace) cudaEventRecord(tev[3 * BE_HOST_CHUNKS], s_in);
     for (int i = 0; i < nchunk; ++i) {
         const int b0 = bounds[i], b1 = bounds[i + 1], nb = b1 - b0;
+        if (nb == 0) continue;                      // more chunks than pairs: nothing to copy or launch
         cudaStream_t s_k = c->st_streams[1];
         BE_CUDA(cudaMemcpyAsync(c->st_est + (size_t)b0 * L * 12, est + (size_t)b0 * L * 12, (size_t)nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaMemcpyAsync(c->st_img + (size_t)b0 * 6 * HW, img + (size_t)b0 * 6 * HW, (size_t)nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));

@@ -65,6 +65,8 @@ struct BeLossArgs {
     const unsigned long long* mask_count;
     BeGeom g;
     int NB, G, runs_per_row;
+    int b0, NBT;                      // global loss: the launch covers pairs [b0, b0 + NB) of targets T laid out for NBT pairs (table, gtable,
+                                      // crec, grad, grad_depth, partials are already offset to pair b0 by the caller)
     float kc, kcc, kbc, ks, ksc, kbl, gamma_d;   // gamma_k / (normaliser_k * N_patches); depth: gamma_d / mask_count
 };
 
@@ -78,14 +80,16 @@ struct BeLossScale {                  // partial sums -> reported terms
 
 // launchers (be_kernels.cu / be_train.cu); all asynchronous on `st`
 void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, float* gtable, cudaStream_t st);
-void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st);
-void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
-                          const float* bndry_depth, float* T, cudaStream_t st);
+// pairs [b0, b0 + nb) of whole-batch arrays laid out for Btot pairs
+void be_launch_train_normalise(const float* acc, const BeGeom& g, int b0, int nb, int Btot, float* T, float* gimg, float* gbnd, cudaStream_t st);
+void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                          const float* deri, const float* bndry_depth, float* T, cudaStream_t st);
 void be_launch_loss(const BeLossArgs& a, cudaStream_t st);               // local-stage loss (be_train.cu)
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
-void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, size_t npatch, cudaStream_t st);
-void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
-                           float* loss, cudaStream_t st);
+void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, const unsigned long long* true_patches,
+                                double assumed_patches, size_t npatch, cudaStream_t st);
+void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count,
+                           const unsigned long long* true_patches, double assumed_patches, float* terms, float* loss, cudaStream_t st);
 void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // renderer + fused fold (be_run3.cu)
 void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st);

@@ -230,10 +230,13 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 o1.x = as * (S[2] + S[3]); o1.y = as * S[3]; o1.z = as * (S[6] + S[7]); o1.w = as * S[7];
                 const float4 zd = make_float4(S[12] * gr[4] * gr[0], S[13] * gr[6] * gr[1], S[12] * gr[5] * gr[2], S[13] * gr[7] * gr[3]);
                 const bool defer = a.defer_depth != 0;                 // depth share kept apart until the batch mask count is known
-                o2.x = S[8] * gr[0] + (defer ? 0.0f : zd.x);
-                o2.y = S[9] * gr[1] + (defer ? 0.0f : zd.y);
-                o2.z = S[10] * gr[2] + (defer ? 0.0f : zd.z);
-                o2.w = S[11] * gr[3] + (defer ? 0.0f : zd.w);
+                // empty batch mask: the reference's depth term is 0/0 and autograd hands NaN to every eta coefficient
+                // (global_training.py:127); the deferred path gets the same from 0 * (1/0) in be_grad_depth_fixup_kernel
+                const float empty = (!defer && *a.mask_count == 0ull) ? __int_as_float(0x7fc00000) : 0.0f;
+                o2.x = S[8] * gr[0] + (defer ? 0.0f : zd.x + empty);
+                o2.y = S[9] * gr[1] + (defer ? 0.0f : zd.y + empty);
+                o2.z = S[10] * gr[2] + (defer ? 0.0f : zd.z + empty);
+                o2.w = S[11] * gr[3] + (defer ? 0.0f : zd.w + empty);
                 float4* o4 = reinterpret_cast<float4*>(a.grad + (patch0 + k) * np);     // 48-byte rows: 16-byte aligned
                 o4[0] = o0; o4[1] = o1; o4[2] = o2;
                 if (defer) reinterpret_cast<float4*>(a.grad_depth)[patch0 + k] = zd;
@@ -278,8 +281,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     const float vm0 = (RCT == BE_MAX_R || valid[0]) ? 1.0f : 0.0f, vm1 = valid[1] ? 1.0f : 0.0f;   // R = 21: every thread has a low pixel
     // depth term: gamma_d / (mask count of the whole batch); with a deferred normaliser (a.grad_depth) the count is applied later
     const float kd = a.defer_depth ? a.gamma_d : a.gamma_d / (float)(*a.mask_count);
-    const unsigned TPS = (unsigned)a.NB * g.H * g.W * 4;   // floats between consecutive float4 planes of T (32-bit offsets: be_launch_loss2 checks the size)
-    const unsigned toff0[2] = {(unsigned)((((size_t)b * g.H + y0 + pi[0]) * g.W + pj[0]) * 4), (unsigned)((((size_t)b * g.H + y0 + pi[1]) * g.W + pj[1]) * 4)};
+    const unsigned TPS = (unsigned)a.NBT * g.H * g.W * 4;   // floats between consecutive float4 planes of T (32-bit offsets: be_launch_loss2 checks the size)
+    const size_t bT = (size_t)(b + a.b0);                   // pair index inside the targets of the whole batch
+    const unsigned toff0[2] = {(unsigned)(((bT * g.H + y0 + pi[0]) * g.W + pj[0]) * 4), (unsigned)(((bT * g.H + y0 + pi[1]) * g.W + pj[1]) * 4)};
     const float k2c = 2.0f * a.kc, k2cc = 2.0f * a.kcc;
 
     float lossacc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

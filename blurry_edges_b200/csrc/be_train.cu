@@ -52,19 +52,22 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __restrict__ acc, BeGeom g, int B,
+// Pairs [b0, b0 + nb) of a workspace laid out for Btot pairs (the host-buffer entry point runs the batch in chunks): `acc`, `T`,
+// `gimg`, `gbnd` are the arrays of the WHOLE batch, the plane stride of T is that of Btot pairs.
+__global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __restrict__ acc, BeGeom g, int b0, int nb, int Btot,
                                                                  float* __restrict__ T, float* __restrict__ gimg,
                                                                  float* __restrict__ gbnd) {
     const size_t HW = (size_t)g.H * g.W;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)B * HW) return;
+    const size_t lidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lidx >= (size_t)nb * HW) return;
+    const size_t idx = lidx + (size_t)b0 * HW;
     const size_t p = idx % HW;
     const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
     const float4* src = reinterpret_cast<const float4*>(acc + idx * 8);
     const float4 q0 = src[0], q1 = src[1];
     const float n = (float)(cover_1d(y, g.R, g.stride, g.Hp) * cover_1d(x, g.R, g.stride, g.Wp));
     const float v[7] = {q0.x / n, q0.y / n, q0.z / n, q0.w / n, q1.x / n, q1.y / n, q1.z / n};
-    const size_t PS = (size_t)B * HW * 4;
+    const size_t PS = (size_t)Btot * HW * 4;
 #pragma unroll
     for (int c = 0; c < 6; ++c) T[t_off(PS, idx, T_GI + c)] = v[c];
     T[t_off(PS, idx, T_GB)] = v[6];
@@ -75,17 +78,18 @@ __global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __
     if (gbnd) gbnd[idx] = v[6];
 }
 
-__global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int B, const float* __restrict__ img_ny,
+__global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int b0, int nb, int Btot, const float* __restrict__ img_ny,
                                                             const float* __restrict__ img_gt, const float* __restrict__ bndry_dist,
                                                             const float* __restrict__ deri, const float* __restrict__ bndry_depth,
                                                             float* __restrict__ T) {
     const bool same_gt = (img_gt == img_ny);          // the GT values are then never read (BeLossArgs::same_gt)
     const size_t HW = (size_t)g.H * g.W;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (size_t)B * HW) return;
+    const size_t lidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lidx >= (size_t)nb * HW) return;
+    const size_t idx = lidx + (size_t)b0 * HW;
     const size_t p = idx % HW;
     const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
-    const size_t PS = (size_t)B * HW * 4;
+    const size_t PS = (size_t)Btot * HW * 4;
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -491,8 +495,11 @@ __global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
 }
 
 // partial sums -> terms (unweighted, as the oracle's `terms`) and the weighted loss
+// `true_patches` (may be NULL): patch count of the global batch as all-reduced over the ranks; sc.scale was computed for
+// `assumed_patches` (local patches x world), so uneven shards are corrected here by assumed / true.
 __global__ void __launch_bounds__(256) be_loss_reduce_kernel(const float* __restrict__ partials, int nblocks, BeLossScale sc,
                                                              const unsigned long long* __restrict__ mask_count,
+                                                             const unsigned long long* __restrict__ true_patches, double assumed_patches,
                                                              float* __restrict__ terms, float* __restrict__ loss) {
     __shared__ double s[256][7];
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -510,9 +517,10 @@ __global__ void __launch_bounds__(256) be_loss_reduce_kernel(const float* __rest
     }
     if (threadIdx.x == 0) {
         double l = 0.0;
+        const double fix = (true_patches != nullptr) ? assumed_patches / (double)(*true_patches) : 1.0;
         for (int t = 0; t < sc.nterms; ++t) {
             const int src = sc.src[t];
-            double v = s[0][src] * sc.scale[t];
+            double v = s[0][src] * sc.scale[t] * fix;
             if (sc.masked[t]) v = s[0][src] / (double)(*mask_count);     // 0/0 -> NaN, as the reference (global_training.py:127)
             terms[t] = (float)v;
             l += (double)sc.gamma[t] * v;
@@ -521,39 +529,49 @@ __global__ void __launch_bounds__(256) be_loss_reduce_kernel(const float* __rest
     }
 }
 
-// deferred depth normaliser: grad[:, 8:12] += grad_depth / (mask count of the whole batch).  An empty mask leaves the gradient
-// alone (its depth share is exactly zero; the loss term itself is 0/0 = NaN as in the reference, global_training.py:127).
+// deferred depth normaliser: grad[:, 8:12] += grad_depth / (mask count of the whole batch).  An empty mask (count 0) behaves like the
+// fused path and like the reference (global_training.py:127, 0/0): the depth share of every patch is 0 * inf = NaN.
+// Uneven data-parallel shards: the kernel's scales assumed `assumed_patches`; the rest of the gradient is corrected by assumed / true.
 __global__ void __launch_bounds__(256) be_grad_depth_fixup_kernel(float* __restrict__ grad, const float4* __restrict__ gd,
-                                                                   const unsigned long long* __restrict__ mask_count, size_t npatch) {
+                                                                   const unsigned long long* __restrict__ mask_count,
+                                                                   const unsigned long long* __restrict__ true_patches, double assumed_patches,
+                                                                   size_t npatch) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npatch) return;
-    const unsigned long long cnt = *mask_count;
-    if (cnt == 0ull) return;
-    const float inv = 1.0f / (float)cnt;
+    const float inv = 1.0f / (float)(*mask_count);          // inf when the batch mask is empty
     const float4 d = gd[i];
-    float4* g = reinterpret_cast<float4*>(grad + i * 12) + 2;
-    float4 v = *g;
+    float4* g = reinterpret_cast<float4*>(grad + i * 12);
+    float4 v = g[2];
+    if (true_patches != nullptr && (double)(*true_patches) != assumed_patches) {
+        const float fix = (float)(assumed_patches / (double)(*true_patches));
+        float4 a = g[0], b = g[1];
+        a.x *= fix; a.y *= fix; a.z *= fix; a.w *= fix; b.x *= fix; b.y *= fix; b.z *= fix; b.w *= fix;
+        v.x *= fix; v.y *= fix; v.z *= fix; v.w *= fix;
+        g[0] = a; g[1] = b;
+    }
     v.x = fmaf(d.x, inv, v.x); v.y = fmaf(d.y, inv, v.y); v.z = fmaf(d.z, inv, v.z); v.w = fmaf(d.w, inv, v.w);
-    *g = v;
+    g[2] = v;
 }
 
 }  // namespace
 
-void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, size_t npatch, cudaStream_t st) {
-    be_grad_depth_fixup_kernel<<<(unsigned)((npatch + 255) / 256), 256, 0, st>>>(grad, reinterpret_cast<const float4*>(grad_depth), mask_count, npatch);
+void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, const unsigned long long* true_patches,
+                                double assumed_patches, size_t npatch, cudaStream_t st) {
+    be_grad_depth_fixup_kernel<<<(unsigned)((npatch + 255) / 256), 256, 0, st>>>(grad, reinterpret_cast<const float4*>(grad_depth), mask_count,
+                                                                                 true_patches, assumed_patches, npatch);
     ++g_be_launches;
 }
 
-void be_launch_train_normalise(const float* acc, const BeGeom& g, int B, float* T, float* gimg, float* gbnd, cudaStream_t st) {
-    const size_t n = (size_t)B * g.H * g.W;
-    be_train_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, B, T, gimg, gbnd);
+void be_launch_train_normalise(const float* acc, const BeGeom& g, int b0, int nb, int Btot, float* T, float* gimg, float* gbnd, cudaStream_t st) {
+    const size_t n = (size_t)nb * g.H * g.W;
+    be_train_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, b0, nb, Btot, T, gimg, gbnd);
     ++g_be_launches;
 }
 
-void be_launch_train_pack(const BeGeom& g, int B, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
-                          const float* bndry_depth, float* T, cudaStream_t st) {
-    const size_t n = (size_t)B * g.H * g.W;
-    be_train_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, B, img_ny, img_gt, bndry_dist, deri, bndry_depth, T);
+void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                          const float* deri, const float* bndry_depth, float* T, cudaStream_t st) {
+    const size_t n = (size_t)nb * g.H * g.W;
+    be_train_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, b0, nb, Btot, img_ny, img_gt, bndry_dist, deri, bndry_depth, T);
     ++g_be_launches;
 }
 
@@ -563,8 +581,8 @@ void be_launch_loss(const BeLossArgs& a, cudaStream_t st) {
     ++g_be_launches;
 }
 
-void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count, float* terms,
-                           float* loss, cudaStream_t st) {
-    be_loss_reduce_kernel<<<1, 256, 0, st>>>(partials, nblocks, sc, mask_count, terms, loss);
+void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count,
+                           const unsigned long long* true_patches, double assumed_patches, float* terms, float* loss, cudaStream_t st) {
+    be_loss_reduce_kernel<<<1, 256, 0, st>>>(partials, nblocks, sc, mask_count, true_patches, assumed_patches, terms, loss);
     ++g_be_launches;
 }

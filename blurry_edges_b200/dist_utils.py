@@ -7,18 +7,22 @@ import torch
 import torch.distributed as dist
 
 
-def sync_loss_normalisers(mask_count: torch.Tensor, local_patches: int, group=None, async_op: bool = False):
-    """Depth-term mask count (global_training.py:127 divides by the count of the WHOLE batch) and patch count of the global
-    batch.  mask_count: int64[1] of this rank, summed in place over `group`.  Returns (mask_count, global_patches); with
-    async_op=True returns (mask_count, global_patches, work) where `work` is the pending all-reduce (None if there was nothing
-    to do): the caller overlaps it with the loss kernel and calls work.wait() before it uses the count."""
+def sync_loss_normalisers(counts: torch.Tensor, local_patches: int, group=None, async_op: bool = False):
+    """Normalisers of the WHOLE batch of a data-parallel loss step, in ONE collective: counts = int64[2] on the device holding
+    (depth-term mask count of this rank, patches of this rank), summed in place over `group` (global_training.py:127 divides by the
+    mask count of the whole batch, the other six terms by the patch count of the whole batch).  A one-element tensor (mask count only)
+    is accepted too.  Returns (counts, assumed_global_patches[, work]): assumed = local_patches * world is what the host can know
+    without waiting for the collective - the kernels are launched with it and `global_loss_stage2_finish` rescales by
+    assumed / counts[1] when the shards turn out to be uneven (a last batch without drop_last).  With async_op=True `work` is the
+    pending all-reduce (None if there was nothing to do): the caller overlaps it with the loss kernel and calls work.wait() before
+    it uses the counts."""
     if group is None and not (dist.is_available() and dist.is_initialized()):
-        return (mask_count, local_patches, None) if async_op else (mask_count, local_patches)
+        return (counts, local_patches, None) if async_op else (counts, local_patches)
     world = dist.get_world_size(group)
     work = None
     if world > 1:
-        work = dist.all_reduce(mask_count, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-    return (mask_count, local_patches * world, work if async_op else None) if async_op else (mask_count, local_patches * world)
+        work = dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return (counts, local_patches * world, work if async_op else None) if async_op else (counts, local_patches * world)
 
 
 def reduce_accumulator(acc: torch.Tensor, group=None, dst_group_rank: int = 0):

@@ -16,22 +16,35 @@ from .fused import _geometry_from_args
 
 
 class _FusedLossFn(torch.autograd.Function):
-    """loss = f(est) with the gradient already computed by the kernel; backward only scales it."""
+    """loss = scale * f(est) with the gradient of f already computed by the kernel; backward only scales it."""
 
     @staticmethod
-    def forward(ctx, est, loss, grad):
+    def forward(ctx, est, loss, grad, scale=1.0):
         ctx.save_for_backward(grad)
-        return loss.reshape(())
+        ctx.scale = scale
+        return loss.reshape(()) if scale == 1.0 else loss.reshape(()) * scale
 
     @staticmethod
     def backward(ctx, gout):
         (grad,) = ctx.saved_tensors
-        return grad * gout, None, None
+        return grad * (gout if ctx.scale == 1.0 else gout * ctx.scale), None, None, None
 
 
 class GlobalLossFused(nn.Module):
-    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None):
+    """Data parallel (`process_group`): every rank holds a slice of the global batch and computes  local sums / normalisers of the
+    WHOLE batch,  so the ranks' values ADD UP to the loss the reference computes on the whole batch in one process.
+      grad_reduce='mean' (default): the returned loss (and its gradient) is multiplied by the number of ranks.  This is the
+          setting for stock DistributedDataParallel, which AVERAGES parameter gradients over the ranks: the averaged gradient is then
+          exactly the reference's whole-batch gradient (so clip_grad_norm_ and AdamW see the reference's step), and the mean over
+          ranks of the returned losses is the reference's loss.
+      grad_reduce='sum': the rank's share is returned unscaled; the caller sums losses / gradients over the ranks itself.
+    `last_loss_share` always holds the unscaled share."""
+
+    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None, grad_reduce='mean'):
         super().__init__()
+        if grad_reduce not in ('mean', 'sum'):
+            raise _lib.BlurryEdgesError(f"grad_reduce must be 'mean' or 'sum', got {grad_reduce!r}")
+        self.grad_reduce = grad_reduce
         self.device = torch.device(device)
         self.depthCal = depthCal
         self.R, self.stride, self.w = int(args.R), int(args.stride), float(args.w)
@@ -111,10 +124,15 @@ class GlobalLossFused(nn.Module):
             grad, gdep = self.ctx.global_loss_stage2_launch(B, self.gammas(), npatch, want_grad)
             work.wait()
             terms, loss, grad = self.ctx.global_loss_stage2_finish(B, self.gammas(), npatch, cnt, grad, gdep)
-        self.global_image, self.global_bndry, self.terms, self.mask_count = gimg, gbnd, terms, cnt
+        self.global_image, self.global_bndry, self.terms, self.mask_count = gimg, gbnd, terms, cnt[:1]
+        self.last_loss_share = loss
+        scale = 1.0
+        if self.process_group is not None and self.grad_reduce == 'mean':
+            import torch.distributed as dist
+            scale = float(dist.get_world_size(self.process_group))
         if want_grad:
-            return _FusedLossFn.apply(est, loss, grad.to(est.dtype))
-        return loss.reshape(())
+            return _FusedLossFn.apply(est, loss, grad.to(est.dtype), scale)
+        return loss.reshape(()) * scale if scale != 1.0 else loss.reshape(())
 
 
 class LocalLossFused(nn.Module):

@@ -131,11 +131,33 @@ int be_global_loss_stage2(be_ctx* ctx, int32_t B, const double* gammas7, int64_t
  * of the eta gradients goes, un-normalised, to dev_grad_depth [B,L,4]; dev_grad and dev_grad_depth are both NULL or both set), so
  * the all-reduce of the count over the ranks overlaps the kernel; `finish`, ordered after the all-reduce, produces terms and loss
  * and adds dev_grad_depth / count to dev_grad[:, :, 8:12].  launch + finish == be_global_loss_stage2 up to fp32 rounding of that
- * last addition.  The same gammas7 / global_patches must be passed to both. */
+ * last addition.  The same gammas7 / global_patches must be passed to both.  Uneven shards: pass global_patches = (local patches) x
+ * (ranks) to both and the all-reduced TRUE patch count of the global batch as dev_true_patches (device int64, may be NULL) to
+ * `finish`, which rescales terms, loss and gradient by assumed / true - the two counts travel in the same 16-byte all-reduce as
+ * the mask count and the loss kernel never waits for it. */
 int be_global_loss_stage2_launch(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, float* dev_grad,
                                  float* dev_grad_depth, void* stream);
 int be_global_loss_stage2_finish(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                                 float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth, void* stream);
+                                 const int64_t* dev_true_patches, float* dev_terms, float* dev_loss, float* dev_grad, float* dev_grad_depth,
+                                 void* stream);
+
+/* Host-buffer form of the training step (global_training.py:208-211 without the network: criteria(est, ...) + backward to est), what
+ * a ctypes binding on the reference side calls with numpy arrays.  All pointers are HOST memory (pinned memory makes the copies
+ * asynchronous) in the dataset layouts of be_global_loss_stage1; img_gt may be the same pointer as img_ny.  The batch is cut into
+ * chunks of pairs: the H2D copy of chunk i+1 overlaps stage 1 and the loss kernel of chunk i (depth normaliser deferred), then one
+ * reduce + depth fix-up and the D2H copy of terms [7], loss [1] and grad [B,L,12] (grad may be NULL).  Synchronous.
+ *   be_host_global_loss            one call, one GPU.
+ *   be_host_global_loss_begin/_end the two halves for data-parallel callers: `begin` leaves the local mask count in dev_mask_count
+ *                                  (DEVICE int64, caller-owned) and issues its kernels on `stream`; the caller all-reduces the count
+ *                                  over the ranks on that stream and passes the global patch count to both halves. */
+int be_host_global_loss(be_ctx* ctx, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                        const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, float* terms7, float* loss1,
+                        float* grad);
+int be_host_global_loss_begin(be_ctx* ctx, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                              const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, int64_t global_patches,
+                              int32_t want_grad, int64_t* dev_mask_count, void* stream);
+int be_host_global_loss_end(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
+                            float* terms7, float* loss1, float* grad, void* stream);
 
 /* LocalLoss.forward + backward (local_training.py:32-52): est [B,10] raw LocalStage output (angles wrapped inside),
  * img_ny / img_gt [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation,
@@ -200,6 +222,9 @@ int be_eval_depth(be_ctx* ctx, const float* dev_depth, const float* dev_gt, int6
  * ms4 = {accumulator memset, be_setup_kernel, be_run3_kernel, be_normalise_kernel}. */
 int be_ctx_set_timing(be_ctx* ctx, int32_t enable);
 int be_ctx_last_timing(be_ctx* ctx, float* ms4);
+/* The same for the training step (be_global_loss_stage1 + stage2, or stage2_launch + stage2_finish): ms7 = {accumulator memset,
+ * be_setup_kernel, be_run3_kernel<TRAINFWD>, be_train_normalise_kernel, be_train_pack_kernel, be_loss2_kernel, reduce (+ depth fix-up)}. */
+int be_ctx_last_train_timing(be_ctx* ctx, float* ms7);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t be_launch_count(void);

@@ -80,3 +80,36 @@ def local_batch(B, R, seed, dtype=torch.float32):
     bd = uniform((B, R, R), seed + 5, 0.0, 6.0, dtype)
     deri = uniform((B, R - 2, R - 2, 3), seed + 6, 0.0, 2.0, dtype)
     return est, ny, gt, bd, deri
+
+
+# ---- basic-shape scenes of the reference's own generator (tests/golden/shapes147.npz, made by tests/golden/make_shapes.py) ----
+_SHAPES = None
+
+
+def shapes_arrays():
+    """The committed fixture as float64 arrays + the derivative maps recomputed from the clean images exactly as the generator
+    defines them (train_val_data_generator.py:111-115: sqrt(Sobel_x^2 + Sobel_y^2) / 255 per channel; interior pixels only, as
+    data/dataset.py:32 keeps them).  The Sobel sums are integers, so the result does not depend on the summation order."""
+    global _SHAPES
+    if _SHAPES is None:
+        import os
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'shapes147.npz'))
+        c = z['clean'].astype(np.float64)                                   # [N,2,H,W,3]
+        gx = (c[:, :, :-2, 2:] - c[:, :, :-2, :-2]) + 2 * (c[:, :, 1:-1, 2:] - c[:, :, 1:-1, :-2]) + (c[:, :, 2:, 2:] - c[:, :, 2:, :-2])
+        gy = (c[:, :, :-2, :-2] + 2 * c[:, :, :-2, 1:-1] + c[:, :, :-2, 2:]) - (c[:, :, 2:, :-2] + 2 * c[:, :, 2:, 1:-1] + c[:, :, 2:, 2:])
+        _SHAPES = {'clean': c, 'noisy': z['noisy'].astype(np.float64), 'dist': z['dist'].astype(np.float64), 'depth': z['depth'],
+                   'alpha': z['alpha'], 'deri': np.sqrt(gx ** 2 + gy ** 2) / 255, 'z': z}
+    return _SHAPES
+
+
+def shapes_batch(B, first=0, dtype=torch.float32):
+    """(img_ny, img_gt [B,2,H,W,3], bndry_dist [B,H,W], deri [B,2,H-2,W-2,3], bndry_depth [B,H,W]) as ShapeDataset(mode='global')
+    hands them to the training loop (data/dataset.py:27-36,50-56: float32 arrays, images divided by alpha); scenes are taken
+    round-robin from the fixture starting at `first`."""
+    a = shapes_arrays()
+    idx = (first + np.arange(B)) % a['clean'].shape[0]
+    f32 = lambda x: torch.from_numpy(x[idx]).float()
+    alpha = f32(a['alpha']).view(B, 1, 1, 1, 1)
+    img_gt = f32(a['clean'] / 255 * a['alpha'][:, None, None, None, None]) / alpha      # images_gt = clean/255*alpha (:175), then /alpha
+    img_ny = f32(a['noisy']) / alpha
+    return tuple(t.to(dtype) for t in (img_ny, img_gt, f32(a['dist']), f32(a['deri']), f32(a['depth'])))

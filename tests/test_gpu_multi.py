@@ -48,7 +48,7 @@ def _train_worker(rank, world, port, out):
                               gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
                               gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
                               gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200])
-    crit = GlobalLossFused(args, None, dev, process_group=dist.group.WORLD)
+    crit = GlobalLossFused(args, None, dev, process_group=dist.group.WORLD, grad_reduce='sum')    # shares that ADD UP
     crit.update_gamma()
     np.testing.assert_allclose(crit.gammas(), gam, rtol=0, atol=0)
     sl = slice(rank, rank + 1)                                       # one sample per rank of the B=2 batch
@@ -89,8 +89,81 @@ def _big_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _gargs(S, B):
+    return argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[S, S], batch_size=B, mag=4.0, cam_params=CAMP,
+                              gamma_color=[1.0, 0.1, 0.1], gamma_color_cons=[0.2, 0.1, 0.05], gamma_bndry_cons=[0.05, 0.05, 0.02],
+                              gamma_smthns=[0.005, 0.1, 0.002], gamma_smthns_cons=[0.005, 0.1, 0.002], gamma_bndry_loc=[0.0001, 0.05, 0.0001],
+                              gamma_depth=[0.0001, 0.05, 0.5], dynamic_epoch=[30, 100, 200])
+
+
+def _uneven_worker(rank, world, port, out):
+    """A last batch without drop_last: rank 0 holds 1 pair, rank 1 holds 2 pairs of a 3-pair batch.  The shares must add up to
+    the single-process loss of the 3-pair batch and every rank's gradient must be its slice of the full gradient: the 16-byte
+    all-reduce carries (mask count, patch count) (global_training.py:127 and the means of :130-139 run over the WHOLE batch)."""
+    _init(rank, world, port)
+    from blurry_edges_b200 import GlobalLossFused
+    from common import F32, GEOMS, gloss_inputs
+    dev = f'cuda:{rank}'
+    S = GEOMS['mid']
+    g, raw, img_ny, img_gt, bd, deri, zgt = [t.to(dev) if torch.is_tensor(t) else t for t in gloss_inputs('mid', 'normal', F32, B=3)]
+    full = GlobalLossFused(_gargs(S, 3), None, dev)
+    full.update_gamma()
+    rf = raw.clone().requires_grad_(True)
+    lf = full(rf, img_ny, img_gt, bd, deri, zgt)
+    lf.backward()
+    sl = slice(0, 1) if rank == 0 else slice(1, 3)
+    crit = GlobalLossFused(_gargs(S, 2), None, dev, process_group=dist.group.WORLD, grad_reduce='sum')
+    crit.update_gamma()
+    rs = raw[sl].clone().requires_grad_(True)
+    ls = crit(rs, img_ny[sl], img_gt[sl], bd[sl], deri[sl], zgt[sl])
+    ls.backward()
+    tot = ls.detach().clone()
+    dist.all_reduce(tot)
+    e_loss = float((tot - lf.detach()).abs() / lf.detach().abs())
+    e_grad = float((rs.grad - rf.grad[sl]).abs().max() / rf.grad.abs().max())
+    out[rank] = (e_loss < 2e-6 and e_grad < 2e-6, e_loss, e_grad)
+    dist.destroy_process_group()
+
+
+def _ddp_worker(rank, world, port, out):
+    """stock DistributedDataParallel AVERAGES parameter gradients.  With the default grad_reduce='mean' the
+    averaged gradients of a stand-in network equal the gradients of a single process holding the whole batch, and the mean of the
+    ranks' losses is the whole-batch loss - so clip_grad_norm_ / AdamW see the reference's step (global_training.py:208-213)."""
+    _init(rank, world, port)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from blurry_edges_b200 import GlobalLossFused
+    from common import F32, GEOMS, gloss_inputs
+    dev = f'cuda:{rank}'
+    S = GEOMS['tiny']
+    g, raw, img_ny, img_gt, bd, deri, zgt = [t.to(dev) if torch.is_tensor(t) else t for t in gloss_inputs('tiny', 'normal', F32, B=2)]
+
+    def make_net():
+        torch.manual_seed(5)
+        return torch.nn.Linear(12, 12).to(dev)                    # stand-in for GlobalStage: est = raw + 0.05 * net(raw)
+
+    net1 = make_net()
+    full = GlobalLossFused(_gargs(S, 2), None, dev)
+    full.update_gamma()
+    l_full = full(raw + 0.05 * net1(raw), img_ny, img_gt, bd, deri, zgt)
+    l_full.backward()
+    net2 = DDP(make_net(), device_ids=[rank])
+    crit = GlobalLossFused(_gargs(S, 1), None, dev, process_group=dist.group.WORLD)          # grad_reduce='mean' is the default
+    crit.update_gamma()
+    sl = slice(rank, rank + 1)
+    l_rank = crit(raw[sl] + 0.05 * net2(raw[sl]), img_ny[sl], img_gt[sl], bd[sl], deri[sl], zgt[sl])
+    l_rank.backward()
+    mean_loss = l_rank.detach().clone()
+    dist.all_reduce(mean_loss)
+    mean_loss /= world
+    e_loss = float((mean_loss - l_full.detach()).abs() / l_full.detach().abs())
+    e_w = float((net2.module.weight.grad - net1.weight.grad).abs().max() / net1.weight.grad.abs().max())
+    e_b = float((net2.module.bias.grad - net1.bias.grad).abs().max() / net1.bias.grad.abs().max())
+    out[rank] = (e_loss < 2e-6 and e_w < 1e-5 and e_b < 1e-5, e_loss, e_w, e_b)
+    dist.destroy_process_group()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
-@pytest.mark.parametrize('worker', [_train_worker, _big_worker])
+@pytest.mark.parametrize('worker', [_train_worker, _big_worker, _uneven_worker, _ddp_worker])
 def test_two_rank_nccl_recipes(worker):
     mgr = mp.Manager()
     out = mgr.dict()

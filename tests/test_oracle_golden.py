@@ -164,3 +164,18 @@ def test_big_235_stitch_against_unchanged_driver():
     assert relmax(out[3][0, 0].numpy()[::st, ::st], gb('big235/bndry')) < 1e-4
     assert relmax(out[5][0].numpy()[::st, ::st], gb('big235/conf')) < 1e-6
     assert relmax(out[6][0].numpy()[::st, ::st], gb('big235/depth_thresholded')) < 1e-5
+
+
+def test_oracle_on_basic_shape_scenes_of_the_reference_generator():
+    """tests/golden/shapes147.npz: two full-size scenes of train_val_data_generator.SyntheticShapeDataGenerator with the golden
+    loss / gradient of the unmodified GlobalLoss (training call: the clean image passed twice, global_training.py:210)."""
+    import synth
+    z = synth.shapes_arrays()['z']
+    g = O.Geometry(H=147, W=147)
+    ny, gt, bd, deri, zg = synth.shapes_batch(2, dtype=torch.float64)
+    assert float(bd.max()) > 10 and float((zg != 0).float().mean()) > 0.02 and float((deri == 0).float().mean()) > 0.5   # a real scene
+    raw = synth.raw_global(2, g.L, seed=81, dtype=torch.float64).requires_grad_(True)
+    loss = O.global_loss(raw, gt, gt, bd, deri, zg, z['gammas'], g, O.Camera())
+    (grad,) = torch.autograd.grad(loss, raw)
+    assert abs(loss.item() - float(z['train.loss'])) <= 1e-10 * abs(loss.item())
+    assert float((grad - torch.from_numpy(z['train.grad'])).abs().max()) <= 1e-9 * float(np.abs(z['train.grad']).max())
