@@ -1,1 +1,15 @@
-"""stub"""
+"""Stand-in for matplotlib.pyplot where matplotlib is absent: utils/util_func.py:30-38 (showCurve) is the only user among the
+reference's scripts; every call is accepted and savefig leaves an empty file so that the scripts' epilogues run through."""
+
+
+class _Fig:
+    def savefig(self, path, *a, **k):
+        open(path, 'wb').close()
+
+
+def gcf():
+    return _Fig()
+
+
+def __getattr__(name):          # figure, xlabel, ylabel, yscale, plot, ...: accepted and ignored
+    return lambda *a, **k: None

@@ -307,9 +307,10 @@ def test_global_loss_step_is_cuda_graph_capturable():
 
 
 def test_empty_depth_mask_matches_autograd_through_the_reference_formula():
-    """bndry_depth == 0 everywhere: the depth term is 0/0 (global_training.py:127).  Autograd through the reference formula hands
-    NaN to the four eta coefficients of every patch and leaves the geometric gradients finite; the library returns the same pattern
-    and the finite part still matches."""
+    """bndry_depth == 0 everywhere: the depth term is 0/0 (global_training.py:127).  Autograd through the reference formula leaves
+    the geometric gradients finite and hands NaN to the eta coefficients of every wedge that owns a mask pixel in its patch (the
+    where() of :88-90 passes exact zeros to the others).  The library - fused and deferred stage 2 alike - returns a NaN loss,
+    NaN for ALL eta-coefficient gradients (a superset: the step is dead either way) and the same finite geometric gradients."""
     from blurry_edges_b200 import GlobalLossFused
     g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('tiny', 'normal', F32)
     gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 0.5]
@@ -321,34 +322,41 @@ def test_empty_depth_mask_matches_autograd_through_the_reference_formula():
     l64 = O.global_loss(r64, img_ny.to(F64), img_gt.to(F64), bd.to(F64), deri.to(F64), z0.to(F64), gam, g, CAM)
     (g64,) = torch.autograd.grad(l64, r64)
     assert np.isnan(loss) and torch.isnan(l64)
-    assert torch.isnan(g64[..., 8:]).all() and torch.isfinite(g64[..., :8]).all()         # what the reference's autograd does
+    assert torch.isfinite(g64[..., :8]).all() and float(torch.isnan(g64[..., 8:]).float().mean()) > 0.5    # the reference's autograd
     assert np.isnan(grad[..., 8:]).all() and np.isfinite(grad[..., :8]).all()
     assert relmax(grad[..., :8], g64[..., :8].numpy()) < 2e-5
 
 
 def test_autograd_nan_corner_case_d_equals_a_equals_zero_is_pinned():
     """utils/postprocessing_loss.py:67-78: where(a < 0, sqrt(d^2 + a^2 w^2) * sgn, d) has a NaN gradient under autograd when a pixel
-    sits exactly on a wedge vertex (d = a = 0: the unselected sqrt branch contributes 0 * inf).  Raw xy = 0 puts both vertices on the
-    centre pixel of the patch.  The library does NOT reproduce the NaN: it returns the gradient with the
-    unselected branch contributing exactly zero - what the reference computes once the sqrt is guarded by the same mask.  Pinned
-    here: (1) the unguarded formula gives NaN for exactly the doctored patches, (2) ours is finite everywhere, (3) ours equals the
-    guarded formula on all patches."""
-    from blurry_edges_b200 import GlobalLossFused
-    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('tiny', 'normal', F32)
-    raw = raw.clone()
-    doctored = [(0, 3), (1, 17)]
-    for b, l in doctored:
-        raw[b, l, :4] = 0.0                                            # restored xy = 3 * 0: vertex on the grid point (10, 10)
-    gam = [1.0, 0.2, 0.05, 0.005, 0.005, 1e-4, 0.5]
-    crit = GlobalLossFused(_gargs(GEOMS['tiny'], 2), None, 'cuda:0')
-    _set_gammas(crit, gam)
-    loss, grad, _ = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
-    a64 = [t.to(F64) for t in (img_ny, img_gt, bd, deri, zgt)]
-    r64 = raw.to(F64).requires_grad_(True)
-    (g_nan,) = torch.autograd.grad(O.global_loss(r64, *a64, gam, g, CAM), r64)
-    bad = torch.isnan(g_nan).any(-1)
-    assert sorted(map(tuple, bad.nonzero().tolist())) == doctored        # (1)
-    assert np.isfinite(grad).all() and np.isfinite(loss)                 # (2)
+    sits exactly on a wedge vertex (d = a = 0: the unselected sqrt branch contributes 0 * inf).  The centre of the fp32 pixel grid
+    is linspace(-1, 1, 21)[10] = -2^-26, which the local-stage parameters (used unscaled, local_training.py:32-36) can hit exactly.
+    The library does NOT reproduce the NaN: it returns the gradient with the unselected branch contributing
+    exactly zero - what the reference computes once the sqrt is guarded by the same mask.  Pinned here: (1) the unguarded formula
+    gives NaN for exactly the doctored patches, (2) ours is finite everywhere, (3) ours equals the guarded formula on all patches."""
+    from blurry_edges_b200 import LocalLossFused
+    g = geom(147)
+    est, ny, gt, bd, deri = synth.local_batch(8, 21, seed=41)
+    est = est.clone()
+    centre = float(torch.linspace(-1, 1, 21)[10])
+    assert centre == -2.0 ** -26
+    doctored = [1, 5]
+    for b in doctored:
+        est[b, :4] = centre
+    betas = (0.001, 0.0005)
+    args = argparse.Namespace(R=21, w=1.0, alpha_lambda=5e-3, batch_size=8, mag=4.0, cam_params=CAMP, beta_bndry_loc=betas[0],
+                              beta_smthns=betas[1], dynamic_epoch=200)
+    crit = LocalLossFused(args, 'cuda:0')
+    crit.final_beta()
+    leaf = est.clone().cuda().requires_grad_(True)
+    loss = crit(leaf * 1.0, ny.cuda(), gt.cuda(), bd.cuda(), deri.cuda())
+    loss.backward()
+    grad = leaf.grad.cpu().numpy()
+    a64 = [t.to(F64) for t in (ny, gt, bd, deri)]
+    e64 = est.to(F64).requires_grad_(True)
+    (g_nan,) = torch.autograd.grad(O.local_loss(e64, *a64, betas, g), e64)
+    assert torch.isnan(g_nan).any(-1).nonzero().flatten().tolist() == doctored      # (1)
+    assert np.isfinite(grad).all() and np.isfinite(loss.item())                      # (2)
     plain_edge = O._edge
 
     def guarded_edge(px, py, ang, X, Y, w):                              # same values; sqrt only ever sees the selected branch
@@ -362,15 +370,19 @@ def test_autograd_nan_corner_case_d_equals_a_equals_zero_is_pinned():
 
     O._edge = guarded_edge
     try:
-        r64 = raw.to(F64).requires_grad_(True)
-        l64 = O.global_loss(r64, *a64, gam, g, CAM)
-        (g64,) = torch.autograd.grad(l64, r64)
+        e64 = est.to(F64).requires_grad_(True)
+        l64 = O.local_loss(e64, *a64, betas, g)
+        (g64,) = torch.autograd.grad(l64, e64)
+        e32 = est.clone().requires_grad_(True)
+        (g32,) = torch.autograd.grad(O.local_loss(e32, ny, gt, bd, deri, betas, g), e32)
     finally:
         O._edge = plain_edge
     assert torch.isfinite(g64).all()
-    assert abs(loss - l64.item()) <= 5e-6 * abs(l64.item())
-    emax, el2 = _grad_err(grad, g64.numpy())
-    assert emax < 5e-5 and el2 < 2e-5, (emax, el2)                        # (3)
+    assert abs(loss.item() - l64.item()) <= 5e-6 * abs(l64.item())
+    floor, _ = _grad_err(g32.numpy(), g64.numpy())
+    emax, _ = _grad_err(grad, g64.numpy())
+    print(f'd=a=0 corner: grad err {emax:.2e}, fp32 autograd floor {floor:.2e}')
+    assert emax < max(2e-5, 2 * floor), (emax, floor)                                # (3)
 
 
 def test_uneven_shards_are_corrected_by_the_true_patch_count():
