@@ -47,6 +47,7 @@ _SIGS = {
     'be_ctx_constants': (C.c_int, [_P, C.POINTER(C.c_double)]),
     'be_derive_constants': (C.c_int, [C.POINTER(BeConfig), C.POINTER(C.c_double)]),
     'be_ctx_set_timing': (C.c_int, [_P, C.c_int32]),
+    'be_ctx_set_deterministic': (C.c_int, [_P, C.c_int32]),
     'be_ctx_last_timing': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'be_cover_count': (C.c_int, [_P, _P, _P]),
     'be_refold_image': (C.c_int, [_P, _P, C.c_int32, _P, _P]),
@@ -200,6 +201,14 @@ class Context:
 
     def workspace_bytes(self):
         return int(self.lib.be_ctx_workspace_bytes(self.h))
+
+    def set_deterministic(self, enable=True):
+        """Fixed-order fold (bit-identical results from launch to launch) instead of the atomic fold; see the header."""
+        enable = bool(enable)
+        if getattr(self, '_det', False) != enable:
+            with torch.cuda.device(self.device):
+                check(self.lib.be_ctx_set_deterministic(self.h, int(enable)))
+            self._det = enable
 
     def set_timing(self, enable=True):
         with torch.cuda.device(self.device):

@@ -95,6 +95,13 @@ class BigImageFused(nn.Module):
         if acc is None:
             acc = torch.zeros(1, self.big_H, self.big_W, 16, device=self.device, dtype=torch.float32)
         blocks = [(0, w[2], w[3], w[4], w[5], w[6], w[7]) for w in self.windows[lo:hi]]
+        if torch.are_deterministic_algorithms_enabled():
+            msg = ('BigImageFused folds the blocks of one image with floating-point atomics and has no deterministic implementation '
+                   '(the reference\'s big-image script does not ask for one)')
+            if not torch.is_deterministic_algorithms_warn_only_enabled():
+                raise _lib.BlurryEdgesError(msg)
+            import warnings
+            warnings.warn(msg)
         if blocks:
             self.ctx.render_fold_blocks(est, img, _lib.planar_layout(self.big_H, self.big_W), blocks, acc)
         return acc

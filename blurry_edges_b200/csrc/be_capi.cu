@@ -73,6 +73,10 @@ struct be_ctx {
     float *ht_raw, *ht_ny, *ht_gt, *ht_bd, *ht_deri, *ht_zg, *ht_grad, *ht_gdep, *ht_scal;
     int ht_want_grad;
     cudaEvent_t tev[BE_TRAIN_EVENTS];   // per-kernel timing of the last training step (be_ctx_last_train_timing)
+    // deterministic fold (be_ctx_set_deterministic): per-patch-row slabs [max_batch][Hp][R][W][accw], allocated on first use
+    int deterministic;
+    float* stage;
+    size_t stage_bytes;
     // optional per-kernel timing of the last be_render_fold_fwd call (be_ctx_set_timing)
     int timing;
     cudaEvent_t ev[5];
@@ -166,6 +170,16 @@ constexpr double RUN_OVH = 5.0, LOSS_OVH = 1.0;   // calibrated: G=64 vs G=32 at
 
 }  // namespace
 
+static int ensure_stage(be_ctx* c, int accw) {
+    const size_t need = (size_t)c->cfg.max_batch * c->g.Hp * c->g.R * c->g.W * accw * sizeof(float);
+    if (c->stage && c->stage_bytes >= need) return 0;
+    if (c->stage) { BE_CUDA(cudaDeviceSynchronize()); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+    if (cudaMalloc(&c->stage, need) != cudaSuccess)
+        return fail("cudaMalloc of the %.1f MiB staging slabs of the deterministic fold failed", need / 1048576.0);
+    c->stage_bytes = need;
+    return 0;
+}
+
 static int ensure_acc(be_ctx* c) {
     if (c->acc) return 0;
     const size_t bytes = (size_t)c->cfg.max_batch * c->g.H * c->g.W * BE_ACC * sizeof(float);
@@ -218,7 +232,7 @@ int be_derive_constants(const be_config* cfg, double* out8) {
 
 int be_ctx_destroy(be_ctx* c) {
     if (!c) return 0;
-    cudaFree(c->table); cudaFree(c->acc);
+    cudaFree(c->table); cudaFree(c->acc); cudaFree(c->stage);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
     cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec);
     cudaFree(c->ht_raw); cudaFree(c->ht_ny); cudaFree(c->ht_gt); cudaFree(c->ht_bd); cudaFree(c->ht_deri); cudaFree(c->ht_zg);
@@ -233,7 +247,13 @@ int be_ctx_destroy(be_ctx* c) {
     return 0;
 }
 
-int64_t be_ctx_workspace_bytes(const be_ctx* c) { return c ? (int64_t)(c->table_bytes + c->acc_bytes + c->st_bytes + c->train_bytes) : 0; }
+int64_t be_ctx_workspace_bytes(const be_ctx* c) { return c ? (int64_t)(c->table_bytes + c->acc_bytes + c->st_bytes + c->train_bytes + c->stage_bytes) : 0; }
+
+int be_ctx_set_deterministic(be_ctx* c, int32_t enable) {
+    if (check_ctx(c)) return 1;
+    c->deterministic = enable ? 1 : 0;
+    return 0;
+}
 
 int be_ctx_constants(const be_ctx* c, double* out8) {
     BE_REQUIRE(c && out8, "null argument");
@@ -305,8 +325,10 @@ static int render_fold_range(be_ctx* c, const float* dev_est, int32_t param_mode
     const int L = g.Hp * g.Wp;
     float* table = c->table + (size_t)b0 * L * BE_REC;
     float* acc = c->acc + (size_t)b0 * g.H * g.W * BE_ACC;
+    const bool det = c->deterministic != 0;
+    if (det && ensure_stage(c, BE_ACC)) return 1;
     if (tm) cudaEventRecord(c->ev[0], st);
-    BE_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * g.H * g.W * BE_ACC * sizeof(float), st));
+    if (!det) BE_CUDA(cudaMemsetAsync(acc, 0, (size_t)B * g.H * g.W * BE_ACC * sizeof(float), st));
     if (tm) cudaEventRecord(c->ev[1], st);
     be_launch_setup(dev_est, param_mode, B * L, c->cam, table, nullptr, st);
     if (tm) cudaEventRecord(c->ev[2], st);
@@ -315,8 +337,13 @@ static int render_fold_range(be_ctx* c, const float* dev_est, int32_t param_mode
     a.table = table; a.img = make_img(dev_img, layout); a.acc = acc;
     a.g = g; a.cam = c->cam; a.NB = B; a.densify_w = densify_w; a.accH = g.H; a.accW = g.W;
     pick_runs(g, B, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+    if (det) {   // one CTA per patch row writes its slab with plain stores; a fixed-order pass folds the slabs into the accumulator
+        a.G = g.Wp; a.runs_per_row = 1;
+        a.stage = c->stage + (size_t)b0 * g.Hp * g.R * g.W * BE_ACC;
+    }
     launch_run(BE_RUN_INFER, a, st);
     if (tm) cudaEventRecord(c->ev[3], st);
+    if (det) be_launch_stage_reduce(a.stage, g, B, BE_ACC, acc, st);
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
     be_launch_normalise(acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
     if (tm) cudaEventRecord(c->ev[4], st);
@@ -372,8 +399,10 @@ static int loss_stage1_range(be_ctx* c, const float* dev_raw, const float* dev_i
     const BeGeom& g = c->g;
     const int L = g.Hp * g.Wp;
     const size_t HW = (size_t)g.H * g.W;
+    const bool det = c->deterministic != 0;
+    if (det && ensure_stage(c, 8)) return 1;
     if (tm) cudaEventRecord(c->tev[0], st);
-    BE_CUDA(cudaMemsetAsync(c->acc + (size_t)b0 * HW * 8, 0, (size_t)nb * HW * 8 * sizeof(float), st));
+    if (!det) BE_CUDA(cudaMemsetAsync(c->acc + (size_t)b0 * HW * 8, 0, (size_t)nb * HW * 8 * sizeof(float), st));
     if (tm) cudaEventRecord(c->tev[1], st);
     be_launch_setup(dev_raw + (size_t)b0 * L * 12, BE_PARAMS_RAW12, nb * L, c->cam, c->table + (size_t)b0 * L * BE_REC,
                     c->gtable + (size_t)b0 * L * BE_GREC, st);
@@ -386,8 +415,13 @@ static int loss_stage1_range(be_ctx* c, const float* dev_raw, const float* dev_i
     a.crec = c->crec + (size_t)b0 * L * BE_CREC;
     a.g = g; a.cam = c->cam; a.NB = nb; a.accH = g.H; a.accW = g.W;
     pick_runs(g, nb, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+    if (det) {
+        a.G = g.Wp; a.runs_per_row = 1;
+        a.stage = c->stage + (size_t)b0 * g.Hp * g.R * g.W * 8;
+    }
     launch_run(BE_RUN_TRAINFWD, a, st);
     if (tm) cudaEventRecord(c->tev[3], st);
+    if (det) be_launch_stage_reduce(a.stage, g, nb, 8, c->acc + (size_t)b0 * HW * 8, st);
     be_launch_train_normalise(c->acc, g, b0, nb, Btot, c->T, dev_global_image, dev_global_bndry, st);
     if (tm) cudaEventRecord(c->tev[4], st);
     be_launch_train_pack(g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
@@ -717,6 +751,7 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     BE_REQUIRE(dev_est && dev_img && dev_acc && blocks, "null pointer");
     BE_REQUIRE(param_mode == BE_PARAMS_RESTORED12 || param_mode == BE_PARAMS_RAW12, "be_render_fold_blocks takes 12-parameter patches");
     BE_REQUIRE(nblk > 0 && nblk <= 2 * c->cfg.max_batch, "nblk=%d exceeds 2*max_batch=%d", nblk, 2 * c->cfg.max_batch);
+    BE_REQUIRE(!c->deterministic, "be_render_fold_blocks has no deterministic (fixed-order) fold: blocks of one image overlap in the accumulator");
     const BeGeom& g = c->g;
     for (int i = 0; i < nblk; ++i)
         BE_REQUIRE(blocks[i].oy + g.H <= acc_H && blocks[i].ox + g.W <= acc_W, "block %d does not fit the %dx%d accumulator", i, acc_H, acc_W);

@@ -48,6 +48,8 @@ struct BeRunArgs {
     float* crec;                      // [NB*L][BE_CREC] colours + inverse normal matrix per patch (TRAINFWD, optional)
     const BeBlock* blocks;            // nullptr: item b is pair/image b at origin (0,0), all patches
     int accH, accW;                   // accumulator plane size (= H, W unless blocked)
+    float* stage;                     // deterministic fold: [NB][Hp][R][W][ACCW] per-patch-row slabs written with plain stores instead of the
+                                      // atomics on `acc` (needs runs_per_row == 1 and no blocks); nullptr = atomic fold
 };
 
 struct BeLossArgs {
@@ -93,6 +95,7 @@ void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale
 void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // renderer + fused fold (be_run3.cu)
 void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st);
+void be_launch_stage_reduce(const float* stage, const BeGeom& g, int B, int accw, float* acc, cudaStream_t st);   // fixed-order fold of the slabs
 void be_launch_refold(const float* unfolded, const BeGeom& g, int M, float* image, cudaStream_t st);
 void be_launch_cover_count(const BeGeom& g, float* out, cudaStream_t st);
 

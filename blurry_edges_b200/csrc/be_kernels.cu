@@ -81,6 +81,30 @@ __global__ void __launch_bounds__(256) be_normalise_kernel(const float* __restri
     if (depth_thr) depth_thr[idx] = (cf > thres) ? dz : 0.0f;
 }
 
+// Deterministic fold, second half: acc[b][y][x][:] = sum over the patch rows py that cover image row y, in ASCENDING py, of the slab
+// cell stage[b][py][y - py*stride][x][:] that the CTA of (b, py) wrote with a plain store (be_run3.cu).  One thread per float4 of a
+// pixel; consecutive threads read consecutive 16 bytes.  The sum order is fixed, so repeated launches are bit-identical
+// (torch.use_deterministic_algorithms, global_training.py:177 / utils/util_func.py:17-19).  Overwrites acc: no memset needed.
+__global__ void __launch_bounds__(256) be_stage_reduce_kernel(const float4* __restrict__ stage, BeGeom g, int B, int q4, float4* __restrict__ acc) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t HW = (size_t)g.H * g.W;
+    if (idx >= (size_t)B * HW * q4) return;
+    const int q = (int)(idx % q4);
+    const size_t pix = idx / q4;
+    const int b = (int)(pix / HW);
+    const int y = (int)((pix % HW) / g.W), x = (int)(pix % g.W);
+    const int hi = min(y / g.stride, g.Hp - 1);
+    const int lo = (y - g.R + 1 <= 0) ? 0 : (y - g.R + g.stride) / g.stride;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x <= (g.Wp - 1) * g.stride + g.R - 1) {
+        for (int py = lo; py <= hi; ++py) {
+            const float4 v = stage[((((size_t)b * g.Hp + py) * g.R + (y - py * g.stride)) * g.W + x) * q4 + q];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    acc[idx] = s;
+}
+
 __global__ void __launch_bounds__(256) be_refold_kernel(const float* __restrict__ unf, BeGeom g, int M, float* __restrict__ img) {
     const size_t HW = (size_t)g.H * g.W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,6 +139,13 @@ void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, 
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st) {
     const size_t n = (size_t)B * g.H * g.W;
     be_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, B, thres, image, sharp, refoc, bndry, depth, conf, depth_thr);
+    ++g_be_launches;
+}
+
+void be_launch_stage_reduce(const float* stage, const BeGeom& g, int B, int accw, float* acc, cudaStream_t st) {
+    const size_t n = (size_t)B * g.H * g.W * (accw / 4);
+    be_stage_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(stage), g, B, accw / 4,
+                                                                        reinterpret_cast<float4*>(acc));
     ++g_be_launches;
 }
 

@@ -408,12 +408,16 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     if (!fl[s]) continue;
-                    float* dst = a.acc + (((size_t)ib * a.accH + oy + y0 + si[s]) * a.accW + ox + (px0 + kp) * g.stride + jc[s]) * ACCW;
+                    // deterministic mode (a.stage): this CTA owns the whole patch row, so every (row-in-patch, column) cell of its slab
+                    // is written exactly once, with a plain store; be_stage_reduce_kernel adds the <= 11 slabs of a pixel in fixed order
+                    float* dst = a.stage ? a.stage + ((((size_t)b * g.Hp + py) * R + si[s]) * g.W + (px0 + kp) * g.stride + jc[s]) * ACCW
+                                         : a.acc + (((size_t)ib * a.accH + oy + y0 + si[s]) * a.accW + ox + (px0 + kp) * g.stride + jc[s]) * ACCW;
 #pragma unroll
                     for (int q = 0; q < ACCW / 4; ++q) {
                         const float4 v = s ? make_float4(hi(acc[4 * q]), hi(acc[4 * q + 1]), hi(acc[4 * q + 2]), hi(acc[4 * q + 3]))
                                            : make_float4(lo(acc[4 * q]), lo(acc[4 * q + 1]), lo(acc[4 * q + 2]), lo(acc[4 * q + 3]));
-                        atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
+                        if (a.stage) reinterpret_cast<float4*>(dst)[q] = v;
+                        else atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) acc[4 * q + e] = s ? mk2(lo(acc[4 * q + e]), 0.0f) : mk2(0.0f, hi(acc[4 * q + e]));
                     }

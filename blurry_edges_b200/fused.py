@@ -11,6 +11,11 @@ import torch.nn as nn
 from . import _lib
 
 
+def want_deterministic(flag):
+    """flag None: follow torch.use_deterministic_algorithms (what utils/util_func.py:17-19 sets for global_training.py:177)."""
+    return torch.are_deterministic_algorithms_enabled() if flag is None else bool(flag)
+
+
 def _geometry_from_args(args):
     H, W = int(args.img_size[0]), int(args.img_size[1])
     return dict(R=int(args.R), stride=int(args.stride), H=H, W=W, w=float(args.w), alpha_lambda=float(args.alpha_lambda),
@@ -30,10 +35,11 @@ class PostProcessFused(nn.Module):
                          (`as_numpy=False` at construction keeps them as device tensors, like the big-image variant).
     """
 
-    def __init__(self, args, depthCal=None, device='cuda:0', as_numpy=True, max_batch=None):
+    def __init__(self, args, depthCal=None, device='cuda:0', as_numpy=True, max_batch=None, deterministic=None):
         super().__init__()
         self.device = torch.device(device)
         self.depthCal = depthCal
+        self.deterministic = deterministic          # None: follow torch.are_deterministic_algorithms_enabled()
         self.R, self.stride, self.w = int(args.R), int(args.stride), float(args.w)
         self.batch_size = int(args.batch_size)
         self.H, self.W = int(args.img_size[0]), int(args.img_size[1])
@@ -99,6 +105,7 @@ class PostProcessFused(nn.Module):
         img, layout = self._as_image(ny_pat, pair=True)
         if img.shape[0] * (1 if img.dim() == 5 else 0.5) != B:
             raise _lib.BlurryEdgesError(f'{B} parameter sets but image tensor {tuple(img.shape)}')
+        self.ctx.set_deterministic(want_deterministic(self.deterministic))
         out = self.ctx.render_fold(est, img, layout, densify_w=(self.densify == 'w'), param_mode=_lib.PARAMS_RESTORED12)
         self.last_depth_thresholded = out[6]
         maps = out[:6]

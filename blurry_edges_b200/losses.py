@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .fused import _geometry_from_args
+from .fused import _geometry_from_args, want_deterministic
 
 
 class _FusedLossFn(torch.autograd.Function):
@@ -40,8 +40,9 @@ class GlobalLossFused(nn.Module):
       grad_reduce='sum': the rank's share is returned unscaled; the caller sums losses / gradients over the ranks itself.
     `last_loss_share` always holds the unscaled share."""
 
-    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None, grad_reduce='mean'):
+    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None, grad_reduce='mean', deterministic=None):
         super().__init__()
+        self.deterministic = deterministic          # None: follow torch.are_deterministic_algorithms_enabled() (global_training.py:177)
         if grad_reduce not in ('mean', 'sum'):
             raise _lib.BlurryEdgesError(f"grad_reduce must be 'mean' or 'sum', got {grad_reduce!r}")
         self.grad_reduce = grad_reduce
@@ -110,6 +111,7 @@ class GlobalLossFused(nn.Module):
         ny, gt = self._f32(img_ny), (img_ny if img_gt is img_ny else img_gt)
         gt = ny if gt is img_ny else self._f32(gt)
         want_grad = torch.is_grad_enabled() and est.requires_grad
+        self.ctx.set_deterministic(want_deterministic(self.deterministic))
         gimg, gbnd, cnt = self.ctx.global_loss_stage1(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self._f32(bndry_depth))
         npatch = B * L
         work = None

@@ -47,6 +47,9 @@ class _SubstituteFused(ABCMeta):
             sub = _fused_for(name, bases, ns)
             if sub is not None:
                 substituted.append((name, sub.__name__))
+                cell = ns.get('__classcell__')          # the body used zero-argument super(): its __class__ cell must name what we return
+                if cell is not None:
+                    cell.cell_contents = sub
                 return sub
         return super().__new__(mcls, name, bases, ns, **kw)
 

@@ -62,6 +62,15 @@ int be_ctx_constants(const be_ctx* ctx, double* out8);
 /* same constants from a config alone; pure host arithmetic, usable without a GPU */
 int be_derive_constants(const be_config* cfg, double* out8);
 
+/* Deterministic fold (torch.use_deterministic_algorithms(True), which global_training.py:177 asks for through
+ * utils/util_func.py:17-19).  By default the fused fold adds overlapping patches with fp32 atomics, so the sums of a pixel arrive in a
+ * run-dependent order (repeated launches agree to ~1e-7, not bit for bit).  With enable != 0, be_render_fold_fwd,
+ * be_host_render_fold and be_global_loss_stage1 / be_host_global_loss* give every patch row ONE thread block, which writes its
+ * overlap sums into a private slab with plain stores; a second kernel adds the <= ceil(R/stride) slabs of every pixel in ascending
+ * patch-row order.  Results are bit-identical from launch to launch; cost: one extra pass over B*Hp*R*W*{16|8} floats.
+ * be_render_fold_blocks refuses to run in this mode. */
+int be_ctx_set_deterministic(be_ctx* ctx, int32_t enable);
+
 /* num_patches of PostProcessGlobalBase (utils/postprocessing_loss.py:139-143), closed form. out [H,W]. */
 int be_cover_count(be_ctx* ctx, float* dev_out, void* stream);
 

@@ -47,7 +47,8 @@ def inference_inputs(gname, kind, dt):
     S = GEOMS[gname]
     g = geom(S)
     img = planar_pair(synth.image_pairs(1, S, S, seed=3, dtype=dt))
-    est = O.restore_global(synth.raw_global(1, g.L, seed=7, kind=kind, dtype=dt))
+    # restored in fp32 as the reference's script does (blurry_edges_test.py:135-138), then cast: every dtype sees the same values
+    est = O.restore_global(synth.raw_global(1, g.L, seed=7, kind=kind, dtype=F32)).to(dt)
     return g, est, img
 
 

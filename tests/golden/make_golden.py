@@ -60,7 +60,9 @@ def gen_inference(out):
                     colors = pp(estA, pat, colors_only=True)                 # blurry_edges_test.py:81-92
                     out[f'{gname}/passA/{tag}'] = np_(colors)
                 for kind in ('normal', 'stress'):
-                    est = restore(synth.raw_global(1, L, seed=7, kind=kind, dtype=dt))
+                    # parameters restored in fp32, as the script does (blurry_edges_test.py:135-138), then cast: the fp64 run of the
+                    # reference sees bit-identical inputs to what the fp32 kernels are fed
+                    est = restore(synth.raw_global(1, L, seed=7, kind=kind, dtype=F32)).to(dt)
                     maps = pp(est, pat, colors_only=False)                   # blurry_edges_test.py:81-100
                     key = f'{gname}/passB/{densify or "none"}/{kind}/{tag}'
                     for n, m in zip(('image', 'sharp', 'refoc', 'bndry', 'depth', 'conf'), maps):

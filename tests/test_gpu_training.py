@@ -467,3 +467,34 @@ def test_basic_shape_scenes_full_size_vs_reference_golden(call):
     fmax, fl2 = _grad_err(z['train32.grad'], z['train.grad'])             # the unmodified reference's own fp32 run against its fp64 run
     print(f'shapes {call}: grad err max {emax:.2e} rel-L2 {el2:.2e}; reference fp32 floor max {fmax:.2e} rel-L2 {fl2:.2e}')
     assert emax < max(1e-5, fmax) and el2 < max(1e-5, fl2), (emax, el2, fmax, fl2)
+
+
+def test_deterministic_fold_is_bit_identical_over_20_launches():
+    """global_training.py:177 -> set_seed(1898, deterministic=True) -> torch.use_deterministic_algorithms(True)
+    (utils/util_func.py:17-19).  GlobalLossFused follows that switch: the fold then runs in fixed order (one CTA per patch row writing a
+    private slab, slabs added in ascending patch-row order) and 20 full-size steps on stress parameters are BIT-identical in loss,
+    gradient and folded maps; the atomic fold agrees with it to reorder noise."""
+    from blurry_edges_b200 import GlobalLossFused
+    S, B = 147, 8
+    g = geom(S)
+    crit = GlobalLossFused(_gargs(S, B), None, 'cuda:0')
+    crit.update_gamma()
+    raw = synth.raw_global(B, g.L, seed=300, kind='stress')
+    img = synth.image_pairs(B, S, S, seed=301)
+    gt, bd, deri, zg = synth.loss_targets(B, S, S, seed=302)
+    l_at, g_at, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
+    gi_at = crit.global_image.clone()
+    torch.use_deterministic_algorithms(True)
+    try:
+        l0, g0, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
+        gi0, gb0 = crit.global_image.clone(), crit.global_bndry.clone()
+        for _ in range(20):
+            l1, g1, _ = _run_global(crit, raw, img, gt, bd, deri, zg)
+            assert l1 == l0 and np.array_equal(g1, g0)
+            assert torch.equal(crit.global_image, gi0) and torch.equal(crit.global_bndry, gb0)
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert abs(l_at - l0) <= 1e-6 * abs(l0) and float(np.abs(g_at - g0).max()) <= 2e-6 * float(np.abs(g0).max())
+    assert float((gi_at - gi0).abs().max()) <= 2e-6
+    l2, _, _ = _run_global(crit, raw, img, gt, bd, deri, zg)                 # the switch is followed both ways
+    assert abs(l2 - l0) <= 1e-6 * abs(l0)
