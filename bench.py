@@ -441,7 +441,11 @@ def extra_configs(args, rank, world, dev, barrier, flush):
     ms = _timed(lambda: bh(est_b, big_img), steps, 3, dev, barrier, world)
     npatch_big = ((big - R) // STRIDE + 1) ** 2
     out['big_1027'] = {'value': npatch_big / (ms / 1e3), 'unit': UNIT, 'ms_per_image': ms, 'blocks': bh.nblk, 'blocks_this_rank': hi - lo,
-                       'scaling': 'strong', 'collective': getattr(bh, 'collective', None) if world > 1 else None}
+                       'scaling': 'strong'}
+    if world > 1:
+        ms_s = _timed(lambda: bh(est_b, big_img, gather=False), steps, 3, dev, barrier, world)
+        out['big_1027'].update(collective='all_to_all of row bands (each rank owns 1/N of the image rows) + gather of the finished bands onto rank 0',
+                               ms_per_image_maps_left_sharded_by_rows=ms_s, value_maps_left_sharded_by_rows=npatch_big / (ms_s / 1e3))
     return out
 
 

@@ -56,8 +56,9 @@ _SIGS = {
                                      _P, _P, _P, _P, _P, _P, _P, _P]),
     'be_colors_blocks_fwd': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.POINTER(BeBlock), C.c_int32, _P, _P]),
     'be_render_fold_blocks': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.POINTER(BeBlock), C.c_int32, C.c_int32,
-                                        C.c_int32, C.c_int32, _P, _P]),
+                                        C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'be_fold_normalise': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'be_fold_normalise_band': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P]),
     'be_params2dists': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P]),
     'be_params2dists_bwd': (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, C.c_int64, _P, _P]),
     'be_dists2indicators': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P]),
@@ -297,22 +298,26 @@ class Context:
                                                 _ptr(out), _stream(self.device)))
         return out
 
-    def render_fold_blocks(self, est, img, layout, blocks, acc, densify_w=False, param_mode=PARAMS_RESTORED12):
-        """adds the blocks' pass-B sums into acc [*,accH,accW,16] (caller-zeroed)"""
+    def render_fold_blocks(self, est, img, layout, blocks, acc, densify_w=False, param_mode=PARAMS_RESTORED12, acc_y0=0):
+        """adds the blocks' pass-B sums into acc [*,rows,accW,16] (caller-zeroed), which holds image rows [acc_y0, acc_y0 + rows)"""
         with torch.cuda.device(self.device):
             check(self.lib.be_render_fold_blocks(self.h, _ptr(est), param_mode, _ptr(img), C.byref(layout), self._blocks(blocks),
-                                                 est.shape[0], int(densify_w), acc.shape[-3], acc.shape[-2], _ptr(acc),
+                                                 est.shape[0], int(densify_w), int(acc_y0), acc.shape[-3], acc.shape[-2], _ptr(acc),
                                                  _stream(self.device)))
         return acc
 
-    def fold_normalise(self, acc, thres):
-        """acc [B,accH,accW,16] -> (image, sharp, refoc, bndry, depth, conf, depth_thresholded) at that size"""
+    def fold_normalise(self, acc, thres, y0=0, full_H=None):
+        """acc [B,rows,accW,16] holding image rows [y0, y0 + rows) of full_H (default: the whole image) ->
+        (image, sharp, refoc, bndry, depth, conf, depth_thresholded) for those rows"""
         B, H, W = acc.shape[0], acc.shape[1], acc.shape[2]
+        full_H = H if full_H is None else int(full_H)
         kw = dict(device=self.device, dtype=torch.float32)
         out = [torch.empty(B, 2, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw),
                torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
-        with torch.cuda.device(self.device):
-            check(self.lib.be_fold_normalise(self.h, _ptr(acc), B, H, W, float(thres), *[_ptr(t) for t in out], _stream(self.device)))
+        if H > 0:
+            with torch.cuda.device(self.device):
+                check(self.lib.be_fold_normalise_band(self.h, _ptr(acc), B, int(y0), H, full_H, W, float(thres), *[_ptr(t) for t in out],
+                                                      _stream(self.device)))
         return out
 
     # ---- training entry points -----------------------------------------------------------

@@ -3,8 +3,10 @@ overlapping blocks; only the interior patch window of every block contributes to
 
 The reference keeps six `full_*` tensors of unfolded patches (6.7 GB at 1027x1027) and folds them at the end.  Here every
 block is rendered straight into ONE interleaved accumulator [1,bigH,bigW,16] at its pixel origin (be_render_fold_blocks),
-so blocks are independent work items: a rank of a multi-GPU job renders a contiguous band of blocks into its own
-accumulator and a single sum-reduce of that accumulator (67 MB at 1027x1027) replaces the gather of unfolded patches."""
+so blocks are independent work items.  A rank of a multi-GPU job renders a contiguous band of blocks into an accumulator that
+covers only the image rows those blocks touch; every rank OWNS a band of image rows, one all_to_all hands each owner the other
+ranks' partial sums for its rows (a few MB per rank, instead of a 67 MB whole-image reduce onto one rank or a 6.7 GB gather of
+unfolded patches), the owner adds them, normalises its band, and the finished bands are gathered (or left sharded)."""
 from __future__ import annotations
 
 import math
@@ -85,15 +87,24 @@ class BigImageFused(nn.Module):
         lay = _lib.single_planar_layout(self.big_H, self.big_W)
         return self.ctx.colors_blocks(est, img, lay, items).view(self.nblk, 2, 3, 3, self.H_patches, self.W_patches)
 
-    def render_partial(self, est, big_img, lo=0, hi=None, acc=None):
-        """Render blocks [lo, hi) (est holds exactly those blocks) into an accumulator [1,bigH,bigW,16]."""
+    def block_rows(self, lo, hi):
+        """Image rows [a, b) that blocks [lo, hi) write: those of their interior patch windows."""
+        if hi <= lo:
+            return (0, 0)
+        ws = self.windows[lo:hi]
+        return (min(w[2] + w[4] * self.stride for w in ws), max(w[2] + (w[5] - 1) * self.stride + self.R for w in ws))
+
+    def render_partial(self, est, big_img, lo=0, hi=None, acc=None, rows=None):
+        """Render blocks [lo, hi) (est holds exactly those blocks) into an accumulator [1,rows,bigW,16] holding image rows `rows` =
+        (a, b) (default: the whole image)."""
         hi = self.nblk if hi is None else hi
+        a, b = (0, self.big_H) if rows is None else rows
         img = self._img(big_img)
         est = est.to(device=self.device, dtype=torch.float32).contiguous()
         if est.shape != (hi - lo, self.L, 12):
             raise _lib.BlurryEdgesError(f'expects est [{hi - lo},{self.L},12], got {tuple(est.shape)}')
         if acc is None:
-            acc = torch.zeros(1, self.big_H, self.big_W, 16, device=self.device, dtype=torch.float32)
+            acc = torch.zeros(1, b - a, self.big_W, 16, device=self.device, dtype=torch.float32)
         blocks = [(0, w[2], w[3], w[4], w[5], w[6], w[7]) for w in self.windows[lo:hi]]
         if torch.are_deterministic_algorithms_enabled():
             msg = ('BigImageFused folds the blocks of one image with floating-point atomics and has no deterministic implementation '
@@ -103,21 +114,31 @@ class BigImageFused(nn.Module):
             import warnings
             warnings.warn(msg)
         if blocks:
-            self.ctx.render_fold_blocks(est, img, _lib.planar_layout(self.big_H, self.big_W), blocks, acc)
+            self.ctx.render_fold_blocks(est, img, _lib.planar_layout(self.big_H, self.big_W), blocks, acc, acc_y0=a)
         return acc
 
-    def finish(self, acc, thres=0.05):
-        """accumulator -> (col_est [1,2,3,H,W], col_shpd, col_refoc, bndry_est, depth, confidence, thresholded depth)."""
-        return tuple(self.ctx.fold_normalise(acc, thres))
+    def finish(self, acc, thres=0.05, y0=0):
+        """accumulator (rows [y0, y0 + acc rows) of the image) -> (col_est [1,2,3,rows,W], col_shpd, col_refoc, bndry_est, depth,
+        confidence, thresholded depth) for those rows."""
+        return tuple(self.ctx.fold_normalise(acc, thres, y0=y0, full_H=self.big_H))
 
-    def forward(self, est, big_img, thres=0.05):
-        """All blocks on this device; with a process_group: est holds this rank's band (see shard_blocks), the partial
-        accumulators are summed onto rank 0, which returns the maps (other ranks return None)."""
+    def forward(self, est, big_img, thres=0.05, gather=True):
+        """All blocks on this device; with a process_group: est holds this rank's band of blocks (see shard_blocks).  The ranks
+        exchange row bands (dist_utils.exchange_row_bands), every rank normalises the band of image rows it owns, and with
+        gather=True rank 0 returns the full maps (other ranks None); gather=False returns (maps of the own band, (y0, y1)) on
+        every rank - the maps stay sharded by rows, e.g. for per-rank device-to-host copies."""
         if self.process_group is None:
             return self.finish(self.render_partial(est, big_img), thres)
         import torch.distributed as dist
-        from .dist_utils import reduce_accumulator
+        from .dist_utils import exchange_row_bands, gather_row_bands, row_bands
         rank, world = dist.get_rank(self.process_group), dist.get_world_size(self.process_group)
+        spans = [self.block_rows(*shard_blocks(self.nblk, r, world)) for r in range(world)]
+        bands = row_bands(self.big_H, world)
         lo, hi = shard_blocks(self.nblk, rank, world)
-        acc = reduce_accumulator(self.render_partial(est, big_img, lo, hi), self.process_group)
-        return self.finish(acc, thres) if rank == 0 else None
+        part = self.render_partial(est, big_img, lo, hi, rows=spans[rank])
+        band = exchange_row_bands(part[0], spans[rank], spans, bands, self.process_group)
+        maps = self.finish(band.unsqueeze(0), thres, y0=bands[rank][0])
+        if not gather:
+            return maps, bands[rank]
+        out = gather_row_bands(maps, bands, self.process_group)
+        return tuple(out) if out is not None else None

@@ -345,7 +345,7 @@ static int render_fold_range(be_ctx* c, const float* dev_est, int32_t param_mode
     if (tm) cudaEventRecord(c->ev[3], st);
     if (det) be_launch_stage_reduce(a.stage, g, B, BE_ACC, acc, st);
     const float thres = densify_w ? 0.0f : 0.05f;   // blurry_edges_test.py:109-112
-    be_launch_normalise(acc, g, B, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
+    be_launch_normalise(acc, g, B, g.H, 0, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr, st);
     if (tm) cudaEventRecord(c->ev[4], st);
     BE_CUDA(cudaGetLastError());
     return 0;
@@ -744,7 +744,7 @@ int be_colors_blocks_fwd(be_ctx* c, const float* dev_est, int32_t param_mode, co
 }
 
 int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, const float* dev_img, const be_image_layout* layout,
-                          const be_block* blocks, int32_t nblk, int32_t densify_w, int32_t acc_H, int32_t acc_W, float* dev_acc,
+                          const be_block* blocks, int32_t nblk, int32_t densify_w, int32_t acc_y0, int32_t acc_H, int32_t acc_W, float* dev_acc,
                           void* stream) {
     if (check_ctx(c) || check_layout(layout)) return 1;
     if (nblk == 0) return 0;
@@ -753,15 +753,20 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     BE_REQUIRE(nblk > 0 && nblk <= 2 * c->cfg.max_batch, "nblk=%d exceeds 2*max_batch=%d", nblk, 2 * c->cfg.max_batch);
     BE_REQUIRE(!c->deterministic, "be_render_fold_blocks has no deterministic (fixed-order) fold: blocks of one image overlap in the accumulator");
     const BeGeom& g = c->g;
-    for (int i = 0; i < nblk; ++i)
-        BE_REQUIRE(blocks[i].oy + g.H <= acc_H && blocks[i].ox + g.W <= acc_W, "block %d does not fit the %dx%d accumulator", i, acc_H, acc_W);
+    for (int i = 0; i < nblk; ++i) {   // the rows a block WRITES: those of its patch window [py0, py1)
+        if (blocks[i].py1 <= blocks[i].py0) continue;
+        const int r0 = blocks[i].oy + blocks[i].py0 * g.stride, r1 = blocks[i].oy + (blocks[i].py1 - 1) * g.stride + g.R;
+        BE_REQUIRE(r0 >= acc_y0 && r1 <= acc_y0 + acc_H && blocks[i].ox + g.W <= acc_W,
+                   "block %d (writes rows %d..%d) does not fit the accumulator (rows %d..%d, %d columns)", i, r0, r1, acc_y0, acc_y0 + acc_H, acc_W);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_blocks(c, blocks, nblk, st)) return 1;
     const int L = g.Hp * g.Wp;
     be_launch_setup(dev_est, param_mode, nblk * L, c->cam, c->table, nullptr, st);
     BeRunArgs a;
     memset(&a, 0, sizeof(a));
-    a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc; a.blocks = c->blk_dev;
+    // the accumulator holds image rows [acc_y0, acc_y0 + acc_H): the kernel addresses it by image row
+    a.table = c->table; a.img = make_img(dev_img, layout); a.acc = dev_acc - (size_t)acc_y0 * acc_W * BE_ACC; a.blocks = c->blk_dev;
     a.g = g; a.cam = c->cam; a.NB = nblk; a.densify_w = densify_w; a.accH = acc_H; a.accW = acc_W;
     pick_runs(g, nblk, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
     launch_run(BE_RUN_INFER, a, st);
@@ -769,21 +774,29 @@ int be_render_fold_blocks(be_ctx* c, const float* dev_est, int32_t param_mode, c
     return 0;
 }
 
-int be_fold_normalise(be_ctx* c, const float* dev_acc, int32_t B, int32_t acc_H, int32_t acc_W, double thres, float* dev_image,
-                      float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf, float* dev_depth_thr,
-                      void* stream) {
+int be_fold_normalise_band(be_ctx* c, const float* dev_acc, int32_t B, int32_t y0, int32_t rows, int32_t full_H, int32_t acc_W, double thres,
+                           float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf,
+                           float* dev_depth_thr, void* stream) {
     if (check_ctx(c)) return 1;
-    if (B == 0) return 0;
+    if (B == 0 || rows == 0) return 0;
     BE_REQUIRE(dev_acc && dev_image && dev_sharp && dev_refoc && dev_bndry && dev_depth && dev_conf, "null pointer");
-    BE_REQUIRE(acc_H >= c->g.R && acc_W >= c->g.R, "accumulator smaller than a patch");
+    BE_REQUIRE(full_H >= c->g.R && acc_W >= c->g.R, "accumulator smaller than a patch");
+    BE_REQUIRE(y0 >= 0 && rows > 0 && y0 + rows <= full_H, "row band [%d, %d) outside the %d rows of the image", y0, y0 + rows, full_H);
     BeGeom g = c->g;
-    g.H = acc_H; g.W = acc_W;
-    g.Hp = (acc_H - g.R) / g.stride + 1;
+    g.H = full_H; g.W = acc_W;
+    g.Hp = (full_H - g.R) / g.stride + 1;
     g.Wp = (acc_W - g.R) / g.stride + 1;
-    be_launch_normalise(dev_acc, g, B, (float)thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr,
+    be_launch_normalise(dev_acc, g, B, rows, y0, (float)thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf, dev_depth_thr,
                         (cudaStream_t)stream);
     BE_CUDA(cudaGetLastError());
     return 0;
+}
+
+int be_fold_normalise(be_ctx* c, const float* dev_acc, int32_t B, int32_t acc_H, int32_t acc_W, double thres, float* dev_image,
+                      float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf, float* dev_depth_thr,
+                      void* stream) {
+    return be_fold_normalise_band(c, dev_acc, B, 0, acc_H, acc_H, acc_W, thres, dev_image, dev_sharp, dev_refoc, dev_bndry, dev_depth, dev_conf,
+                                  dev_depth_thr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -93,7 +93,7 @@ void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsi
 void be_launch_loss_reduce(const float* partials, int nblocks, const BeLossScale& sc, const unsigned long long* mask_count,
                            const unsigned long long* true_patches, double assumed_patches, float* terms, float* loss, cudaStream_t st);
 void be_launch_run3(int mode, const BeRunArgs& a, cudaStream_t st);   // renderer + fused fold (be_run3.cu)
-void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
+void be_launch_normalise(const float* acc, const BeGeom& g, int B, int rows, int y_first, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st);
 void be_launch_stage_reduce(const float* stage, const BeGeom& g, int B, int accw, float* acc, cudaStream_t st);   // fixed-order fold of the slabs
 void be_launch_refold(const float* unfolded, const BeGeom& g, int M, float* image, cudaStream_t st);

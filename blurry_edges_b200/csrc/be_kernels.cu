@@ -51,17 +51,19 @@ __device__ __forceinline__ int cover_1d(int y, int R, int s, int np) {
     return max(hi - lo + 1, 0);
 }
 
-__global__ void __launch_bounds__(256) be_normalise_kernel(const float* __restrict__ acc, BeGeom g, int B, float thres,
+// `rows`, `y_first`: the accumulator (and the outputs) hold image rows [y_first, y_first + rows) of the g.H rows of the image - the
+// whole image (rows = g.H, y_first = 0) or the row band one rank of a block-sharded big-image job owns.
+__global__ void __launch_bounds__(256) be_normalise_kernel(const float* __restrict__ acc, BeGeom g, int B, int rows, int y_first, float thres,
                                                            float* __restrict__ image, float* __restrict__ sharp,
                                                            float* __restrict__ refoc, float* __restrict__ bndry,
                                                            float* __restrict__ depth, float* __restrict__ conf,
                                                            float* __restrict__ depth_thr) {
-    const size_t HW = (size_t)g.H * g.W;
+    const size_t HW = (size_t)rows * g.W;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * HW) return;
     const int b = (int)(idx / HW);
     const size_t p = idx % HW;
-    const int y = (int)(p / g.W), x = (int)(p % g.W);
+    const int y = y_first + (int)(p / g.W), x = (int)(p % g.W);
     const float4* src = reinterpret_cast<const float4*>(acc + idx * BE_ACC);
     const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
     const float n = (float)(cover_1d(y, g.R, g.stride, g.Hp) * cover_1d(x, g.R, g.stride, g.Wp));
@@ -135,10 +137,11 @@ void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& 
     ++g_be_launches;
 }
 
-void be_launch_normalise(const float* acc, const BeGeom& g, int B, float thres, float* image, float* sharp, float* refoc,
+void be_launch_normalise(const float* acc, const BeGeom& g, int B, int rows, int y_first, float thres, float* image, float* sharp, float* refoc,
                          float* bndry, float* depth, float* conf, float* depth_thr, cudaStream_t st) {
-    const size_t n = (size_t)B * g.H * g.W;
-    be_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, B, thres, image, sharp, refoc, bndry, depth, conf, depth_thr);
+    const size_t n = (size_t)B * rows * g.W;
+    be_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, B, rows, y_first, thres, image, sharp, refoc, bndry, depth, conf,
+                                                                     depth_thr);
     ++g_be_launches;
 }
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BE_ABI_VERSION 1
+#define BE_ABI_VERSION 2
 
 /* how a patch's parameter vector is encoded (see be_math.cuh) */
 #define BE_PARAMS_RESTORED12 0   /* xy, wrapped angles, eta coefficients: what blurry_edges_test.py:135-138 builds */
@@ -107,18 +107,24 @@ int be_host_render_fold(be_ctx* ctx, const float* est, int32_t param_mode, const
  * rendered (the 10-patch margins are dropped except at the image border, :166-177).
  * be_colors_blocks_fwd: pass A for nitem (block, image) items; est [nitem,L,10] -> colours [nitem,3,3,Hp,Wp].
  * be_render_fold_blocks: pass B of nblk blocks (est [nblk,L,12]) ADDED into a caller-owned, caller-zeroed accumulator
- *   [*,acc_H,acc_W,16] at the blocks' origins - the per-block patch grids are never stitched or unfolded.  Ranks of a
- *   multi-GPU job render disjoint block subsets into their own accumulators and sum them (one reduce of 16 planes).
- * be_fold_normalise: accumulator [B,acc_H,acc_W,16] -> the six maps (+ thresholded depth) at that size (:185-190). */
+ *   [*,acc_H,acc_W,16] that holds image rows [acc_y0, acc_y0 + acc_H), at the blocks' origins - the per-block patch grids are never
+ *   stitched or unfolded.  Ranks of a multi-GPU job render contiguous bands of blocks into accumulators that cover only the rows
+ *   their blocks touch, then exchange row bands (each rank OWNS a band of image rows: it receives the other ranks' partial sums
+ *   for those rows, adds them and normalises its band).
+ * be_fold_normalise: accumulator [B,acc_H,acc_W,16] -> the six maps (+ thresholded depth) at that size (:185-190).
+ * be_fold_normalise_band: the same for rows [y0, y0 + rows) of an image of full_H rows (accumulator and outputs hold the band). */
 typedef struct be_block { int32_t img, oy, ox, py0, py1, px0, px1; } be_block;
 int be_colors_blocks_fwd(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
                          const be_image_layout* layout, const be_block* blocks, int32_t nitem, float* dev_colors, void* stream);
 int be_render_fold_blocks(be_ctx* ctx, const float* dev_est, int32_t param_mode, const float* dev_img,
                           const be_image_layout* layout, const be_block* blocks, int32_t nblk, int32_t densify_w,
-                          int32_t acc_H, int32_t acc_W, float* dev_acc, void* stream);
+                          int32_t acc_y0, int32_t acc_H, int32_t acc_W, float* dev_acc, void* stream);
 int be_fold_normalise(be_ctx* ctx, const float* dev_acc, int32_t B, int32_t acc_H, int32_t acc_W, double thres,
                       float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf,
                       float* dev_depth_thresholded, void* stream);
+int be_fold_normalise_band(be_ctx* ctx, const float* dev_acc, int32_t B, int32_t y0, int32_t rows, int32_t full_H, int32_t acc_W, double thres,
+                           float* dev_image, float* dev_sharp, float* dev_refoc, float* dev_bndry, float* dev_depth, float* dev_conf,
+                           float* dev_depth_thresholded, void* stream);
 
 /* GlobalLoss.forward + backward (global_training.py:62-157), in two stages so that a data-parallel caller can all-reduce
  * the depth-term normaliser between them (the depth term divides by the mask count of the WHOLE batch, :127).

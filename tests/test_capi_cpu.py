@@ -28,7 +28,7 @@ def test_header_and_binding_agree(lib):
 
 
 def test_abi_version(lib):
-    assert lib.be_abi_version() == 1
+    assert lib.be_abi_version() == 2
 
 
 def test_derived_constants_match_reference_formulas(lib):

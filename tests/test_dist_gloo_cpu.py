@@ -1,7 +1,8 @@
 """world_size-2 gloo tests (CPU) of the two multi-GPU recipes of the path, with the oracle doing the arithmetic:
   * training: ranks hold disjoint halves of the batch, all-reduce the depth-term mask count, normalise by the global
     patch count -> the ranks' losses add up to the unmodified reference's full-batch loss (golden vector);
-  * big image: ranks render contiguous bands of blocks into partial accumulators, one sum-reduce -> the stitched maps."""
+  * big image: ranks render contiguous bands of blocks into partial accumulators over the rows they touch, one all_to_all hands
+    every rank the partial sums of the row band it owns -> that band of the stitched maps."""
 import os
 import socket
 
@@ -61,15 +62,22 @@ def _big_worker(rank, world, port, out):
     _init(rank, world, port)
     import synth
     from blurry_edges_b200.big import block_windows, shard_blocks
-    from blurry_edges_b200.dist_utils import reduce_accumulator
+    from blurry_edges_b200.dist_utils import exchange_row_bands, row_bands
     from common import F64, geom, planar_pair
     from oracle import be_oracle as O
     big, g, cam = 235, geom(147), O.Camera()
     img = planar_pair(torch.from_numpy(synth.photon_pairs(1, big, big, seed=61)).to(F64) / 190.0)[0]
     est = torch.stack([O.restore_global(synth.raw_global(1, g.L, seed=70 + k, dtype=F64))[0] for k in range(4)])
     wins = block_windows(big, big, 147, 147, 21, 2, 10)
+    # the row spans every rank's blocks write and the row bands the ranks own (BigImageFused.forward does the same on the device)
+    def rows_of(lo_, hi_):
+        ws = wins[lo_:hi_]
+        return (min(w[2] + 2 * w[4] for w in ws), max(w[2] + 2 * (w[5] - 1) + 21 for w in ws)) if ws else (0, 0)
+    spans = [rows_of(*shard_blocks(len(wins), r, world)) for r in range(world)]
+    bands = row_bands(big, world)
     lo, hi = shard_blocks(len(wins), rank, world)
-    acc = torch.zeros(1, big, big, 4, dtype=F64)                      # planes: image0 r,g,b + boundary (enough to check the recipe)
+    a, b = spans[rank]
+    acc = torch.zeros(b - a, big, 4, dtype=F64)                       # planes: image0 r,g,b + boundary (enough to check the recipe)
     for k in range(lo, hi):
         iv, ih, oy, ox, py0, py1, px0, px1 = wins[k]
         r = O.inference(est[k:k + 1], img[None, :, :, oy:oy + 147, ox:ox + 147], g, cam, return_patches=True)
@@ -77,26 +85,25 @@ def _big_worker(rank, world, port, out):
         lb = r['lb'].reshape(g.Hp, g.Wp, 21, 21)
         for py in range(py0, py1):
             for px in range(px0, px1):
-                y, x = oy + 2 * py, ox + 2 * px
-                acc[0, y:y + 21, x:x + 21, :3] += P1[py, px].permute(1, 2, 0)
-                acc[0, y:y + 21, x:x + 21, 3] += lb[py, px]
-    reduce_accumulator(acc, None)
-    if rank == 0:
-        ref = O.inference_big(est, img, g, cam, big, big)
-        n = O.cover_count(O.Geometry(H=big, W=big), F64)
-        ok = torch.allclose(acc[0, :, :, :3].permute(2, 0, 1) / n, ref[0][0, 0], rtol=0, atol=1e-10) and \
-            torch.allclose(acc[0, :, :, 3] / n, ref[3][0, 0], rtol=0, atol=1e-10)
-        out[0] = bool(ok)
-    out[rank] = out.get(rank, True)
+                y, x = oy + 2 * py - a, ox + 2 * px
+                acc[y:y + 21, x:x + 21, :3] += P1[py, px].permute(1, 2, 0)
+                acc[y:y + 21, x:x + 21, 3] += lb[py, px]
+    band = exchange_row_bands(acc, spans[rank], spans, bands, None)   # ONE all_to_all: every owner gets the partial sums of its rows
+    y0, y1 = bands[rank]
+    ref = O.inference_big(est, img, g, cam, big, big)
+    n = O.cover_count(O.Geometry(H=big, W=big), F64)[y0:y1]
+    ok = torch.allclose(band[:, :, :3].permute(2, 0, 1) / n, ref[0][0, 0][:, y0:y1], rtol=0, atol=1e-10) and \
+        torch.allclose(band[:, :, 3] / n, ref[3][0, 0][y0:y1], rtol=0, atol=1e-10)
+    out[rank] = bool(ok)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('worker', [_train_worker, _big_worker])
-def test_two_rank_recipes(worker):
+@pytest.mark.parametrize('worker,world', [(_train_worker, 2), (_big_worker, 2), (_big_worker, 3)])
+def test_multi_rank_recipes(worker, world):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    assert dict(out) == {0: True, 1: True}
+    mp.spawn(worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert dict(out) == {r: True for r in range(world)}
 
 
 def test_numa_binding_helper_is_harmless_without_a_gpu():
