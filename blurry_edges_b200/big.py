@@ -135,10 +135,12 @@ class BigImageFused(nn.Module):
         spans = [self.block_rows(*shard_blocks(self.nblk, r, world)) for r in range(world)]
         bands = row_bands(self.big_H, world)
         lo, hi = shard_blocks(self.nblk, rank, world)
-        part = self.render_partial(est, big_img, lo, hi, rows=spans[rank])
-        band = exchange_row_bands(part[0], spans[rank], spans, bands, self.process_group)
+        span = spans[rank] if hi > lo else (bands[rank][0], bands[rank][0])
+        rows = (min(span[0], bands[rank][0]), max(span[1], bands[rank][1]))      # one accumulator over the rows written and the rows owned
+        part = self.render_partial(est, big_img, lo, hi, rows=rows)
+        band = exchange_row_bands(part[0], rows, span, spans, bands, self.process_group)
         maps = self.finish(band.unsqueeze(0), thres, y0=bands[rank][0])
         if not gather:
             return maps, bands[rank]
-        out = gather_row_bands(maps, bands, self.process_group)
+        out = gather_row_bands(maps, bands, group=self.process_group)
         return tuple(out) if out is not None else None

@@ -601,12 +601,34 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
     BE_CUDA(cudaEventRecord(c->st_events[2 * BE_HOST_CHUNKS - 1], s_k));
     BE_CUDA(cudaStreamWaitEvent(s_in, c->st_events[2 * BE_HOST_CHUNKS - 1], 0));
     BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), s_k));
-    static const int want = [] { const char* e = getenv("BE_HOST_TRAIN_CHUNKS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > BE_HOST_CHUNKS - 1 ? BE_HOST_CHUNKS - 1 : v); }();
-    const int nchunk = B < want ? B : want;
+    // Chunks grow 1:3:5:7: a small first chunk gets the kernels going after ~6 % of the H2D traffic, the later chunks are large enough
+    // to fill whole waves of CTAs (a chunk of n pairs costs at least one wave: ~0.2 ms), and every chunk's copy is done before the
+    // kernels of the previous ones are (H2D 45 MB ~ 0.9 ms, kernels 2.9 ms at 32 pairs).  BE_HOST_TRAIN_WGT="a,b,c,..." overrides.
+    static int wgt[BE_HOST_CHUNKS] = {1, 3, 5, 7};
+    static int nw = 4;
+    static const bool parsed = [] {
+        const char* e = getenv("BE_HOST_TRAIN_WGT");
+        if (e) {
+            int k = 0;
+            while (*e && k < BE_HOST_CHUNKS - 1) { const int v = atoi(e); wgt[k++] = v < 1 ? 1 : v; while (*e && *e != ',') ++e; if (*e == ',') ++e; }
+            if (k > 0) nw = k;
+        }
+        return true;
+    }();
+    (void)parsed;
+    int bounds[BE_HOST_CHUNKS + 1];
+    int nchunk = nw;
+    {
+        int tot_w = 0, acc_w = 0;
+        for (int i = 0; i < nw; ++i) tot_w += wgt[i];
+        bounds[0] = 0;
+        for (int i = 0; i < nw; ++i) { acc_w += wgt[i]; bounds[i + 1] = (int)(((long long)B * acc_w + tot_w / 2) / tot_w); }
+        bounds[nw] = B;
+    }
     int part_off = 0;
     for (int i = 0; i < nchunk; ++i) {
-        const int b0 = (int)((long long)B * i / nchunk), b1 = (int)((long long)B * (i + 1) / nchunk), nb = b1 - b0;
-        if (nb == 0) continue;
+        const int b0 = bounds[i], b1 = bounds[i + 1], nb = b1 - b0;
+        if (nb <= 0) continue;
         BE_CUDA(cudaMemcpyAsync(c->ht_raw + b0 * L * 12, raw + b0 * L * 12, nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaMemcpyAsync(c->ht_ny + b0 * 6 * HW, img_ny + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
         if (!same) BE_CUDA(cudaMemcpyAsync(c->ht_gt + b0 * 6 * HW, img_gt + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));

@@ -36,55 +36,73 @@ def row_bands(H: int, world: int):
     return out
 
 
-def exchange_row_bands(acc_local: torch.Tensor, span, spans, bands, group=None):
-    """Big-image block sharding, the one exchange step.  Every rank has folded its blocks into `acc_local` [rows, W, C], the partial
-    sums of image rows span = [a, b) (only the rows its blocks touch); spans / bands list every rank's span and owned band.  ONE
-    all_to_all_single sends each owner exactly the rows of its band that this rank touched (consecutive owners -> contiguous slices of
-    acc_local: no packing) and returns the owner's band accumulator [band rows, W, C] = the sum of the received pieces.  A rank
-    ships its own rows (<= 3 block rows) instead of the whole image that a reduce onto one rank moved (67.5 MB at 1027 x 1027)."""
+def exchange_row_bands(acc: torch.Tensor, acc_rows, span, spans, bands, group=None):
+    """Big-image block sharding, the one exchange step.  Every rank has folded its blocks into `acc` [rows, W, C], which holds image
+    rows acc_rows = [r0, r1) - an interval that contains both span = [a, b), the rows its blocks wrote, and the band of rows the
+    rank OWNS; spans / bands list every rank's span and band.  ONE all_to_all_single sends each other owner exactly the rows of its
+    band that this rank wrote (consecutive owners -> contiguous slices of acc: no packing) and the received pieces are added IN PLACE
+    to the rank's own rows of acc (fixed source order).  Returns the view acc[own band] - complete sums, ready to be normalised.
+    A rank ships the few rows it shares with its neighbours instead of the whole image that a reduce onto one rank moved
+    (67.5 MB at 1027 x 1027), and its own rows never move."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    W, C = acc_local.shape[-2], acc_local.shape[-1]
+    W, C = acc.shape[-2], acc.shape[-1]
     cut = lambda sp, bd: (max(sp[0], bd[0]), max(min(sp[1], bd[1]), max(sp[0], bd[0])))       # rows of span sp inside band bd (may be empty)
-    send = [cut(span, bands[o]) for o in range(world)]
-    recv = [cut(spans[s], bands[rank]) for s in range(world)]
+    send = [cut(span, bands[o]) if o != rank else (span[0], span[0]) for o in range(world)]
+    recv = [cut(spans[s], bands[rank]) if s != rank else (0, 0) for s in range(world)]
     in_split = [(y1 - y0) * W * C for y0, y1 in send]
     out_split = [(y1 - y0) * W * C for y0, y1 in recv]
-    first = min((y0 for y0, y1 in send if y1 > y0), default=span[0])
-    last = max((y1 for y0, y1 in send if y1 > y0), default=span[0])
-    src = acc_local.reshape(-1)[(first - span[0]) * W * C:(last - span[0]) * W * C]
-    got = torch.empty(sum(out_split), dtype=acc_local.dtype, device=acc_local.device)
+    r0 = acc_rows[0]
+    # rows sent to owners below this rank, then rows sent to owners above it: two contiguous runs of acc; all_to_all_single wants one
+    # contiguous input in rank order, so the (at most two) runs are concatenated - a few shared rows, not the accumulator
+    lowr = [(y0, y1) for o, (y0, y1) in enumerate(send) if o < rank and y1 > y0]
+    high = [(y0, y1) for o, (y0, y1) in enumerate(send) if o > rank and y1 > y0]
+    parts = []
+    for runs in (lowr, high):
+        if runs:
+            parts.append(acc[min(y0 for y0, _ in runs) - r0:max(y1 for _, y1 in runs) - r0].reshape(-1))
+    src = parts[0] if len(parts) == 1 else (torch.cat(parts) if parts else acc.new_empty(0))
+    got = torch.empty(sum(out_split), dtype=acc.dtype, device=acc.device)
     dist.all_to_all_single(got, src.contiguous(), out_split, in_split, group=group)
-    y0b, y1b = bands[rank]
-    band = torch.zeros(y1b - y0b, W, C, dtype=acc_local.dtype, device=acc_local.device)
     off = 0
     for (y0, y1), n in zip(recv, out_split):                                                  # fixed source order: rank 0, 1, ...
         if n:
-            band[y0 - y0b:y1 - y0b] += got[off:off + n].view(y1 - y0, W, C)
+            acc[y0 - r0:y1 - r0] += got[off:off + n].view(y1 - y0, W, C)
         off += n
-    return band
+    y0b, y1b = bands[rank]
+    return acc[y0b - r0:y1b - r0]
 
 
-def gather_row_bands(maps, bands, group=None, dst_group_rank: int = 0):
-    """The finished maps of every rank's band ([..., band rows, W] tensors) -> full-height maps on one rank (None elsewhere)."""
+def gather_row_bands(maps, bands, out=None, group=None, dst_group_rank: int = 0):
+    """The finished maps of every rank's band ([..., band rows, W] tensors) -> full-height maps on one rank (None elsewhere).  Every
+    (plane, band) is a contiguous run of rows of the destination plane, so the bands are received straight into place with one
+    grouped batch of point-to-point transfers: no packing, no concatenation."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    hmax = max(y1 - y0 for y0, y1 in bands)
     W = maps[0].shape[-1]
+    H = bands[-1][1]
     planes = [m.reshape(-1, m.shape[-2], W) for m in maps]
-    pack = torch.zeros(sum(p.shape[0] for p in planes), hmax, W, dtype=maps[0].dtype, device=maps[0].device)
-    pack[:, :planes[0].shape[1]] = torch.cat(planes, 0)
-    dst = dist.get_global_rank(group, dst_group_rank) if group is not None else dst_group_rank
-    lst = [torch.empty_like(pack) for _ in range(world)] if rank == dst_group_rank else None
-    dist.gather(pack, lst, dst=dst, group=group)
-    if rank != dst_group_rank:
-        return None
-    full = torch.cat([t[:, :y1 - y0] for t, (y0, y1) in zip(lst, bands)], 1)                  # [planes, H, W]
-    out, k = [], 0
-    for m in maps:
-        n = m.numel() // (m.shape[-2] * W)
-        out.append(full[k:k + n].reshape(tuple(m.shape[:-2]) + (full.shape[1], W)))
-        k += n
-    return out
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    ops = []
+    if rank == dst_group_rank:
+        if out is None:
+            out = [torch.empty(tuple(m.shape[:-2]) + (H, W), dtype=m.dtype, device=m.device) for m in maps]
+        full = [o.view(-1, H, W) for o in out]
+        for s, (y0, y1) in enumerate(bands):
+            for f, p in zip(full, planes):
+                for k in range(f.shape[0]):
+                    if s == rank:
+                        f[k, y0:y1].copy_(p[k])
+                    elif y1 > y0:
+                        ops.append(dist.P2POp(dist.irecv, f[k, y0:y1], glob(s), group))
+    else:
+        for p in planes:
+            for k in range(p.shape[0]):
+                if p.shape[1] > 0:
+                    ops.append(dist.P2POp(dist.isend, p[k], glob(dst_group_rank), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out if rank == dst_group_rank else None
 
 
 def bind_to_gpu_numa_node(device_index: int) -> dict:

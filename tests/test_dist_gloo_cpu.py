@@ -76,8 +76,9 @@ def _big_worker(rank, world, port, out):
     spans = [rows_of(*shard_blocks(len(wins), r, world)) for r in range(world)]
     bands = row_bands(big, world)
     lo, hi = shard_blocks(len(wins), rank, world)
-    a, b = spans[rank]
-    acc = torch.zeros(b - a, big, 4, dtype=F64)                       # planes: image0 r,g,b + boundary (enough to check the recipe)
+    rows = (min(spans[rank][0], bands[rank][0]), max(spans[rank][1], bands[rank][1]))      # rows written + rows owned
+    a = rows[0]
+    acc = torch.zeros(rows[1] - rows[0], big, 4, dtype=F64)           # planes: image0 r,g,b + boundary (enough to check the recipe)
     for k in range(lo, hi):
         iv, ih, oy, ox, py0, py1, px0, px1 = wins[k]
         r = O.inference(est[k:k + 1], img[None, :, :, oy:oy + 147, ox:ox + 147], g, cam, return_patches=True)
@@ -88,12 +89,20 @@ def _big_worker(rank, world, port, out):
                 y, x = oy + 2 * py - a, ox + 2 * px
                 acc[y:y + 21, x:x + 21, :3] += P1[py, px].permute(1, 2, 0)
                 acc[y:y + 21, x:x + 21, 3] += lb[py, px]
-    band = exchange_row_bands(acc, spans[rank], spans, bands, None)   # ONE all_to_all: every owner gets the partial sums of its rows
+    band = exchange_row_bands(acc, rows, spans[rank], spans, bands, None)   # ONE all_to_all: every owner gets the partial sums of its rows
     y0, y1 = bands[rank]
     ref = O.inference_big(est, img, g, cam, big, big)
     n = O.cover_count(O.Geometry(H=big, W=big), F64)[y0:y1]
     ok = torch.allclose(band[:, :, :3].permute(2, 0, 1) / n, ref[0][0, 0][:, y0:y1], rtol=0, atol=1e-10) and \
         torch.allclose(band[:, :, 3] / n, ref[3][0, 0][y0:y1], rtol=0, atol=1e-10)
+    # the finished bands are received straight into place on rank 0 (one grouped batch of point-to-point transfers)
+    from blurry_edges_b200.dist_utils import gather_row_bands
+    mine = [(band[:, :, :3].permute(2, 0, 1) / n).unsqueeze(0).contiguous(), (band[:, :, 3] / n).contiguous()]
+    full = gather_row_bands(mine, bands)
+    if rank == 0:
+        ok = ok and torch.allclose(full[0][0], ref[0][0, 0], rtol=0, atol=1e-10) and torch.allclose(full[1], ref[3][0, 0], rtol=0, atol=1e-10)
+    else:
+        ok = ok and full is None
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
