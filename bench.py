@@ -420,7 +420,22 @@ def extra_configs(args, rank, world, dev, barrier, flush):
         lcrit(le, lny, lgt, lbd, lderi).backward()
 
     ms = _timed(local_step, max(steps, 10), 3, dev, barrier, world)
-    out['local_train_step'] = {'value': Bl * world / (ms / 1e3), 'unit': 'single patches/s', 'ms_per_step': ms, 'patches_per_gpu': Bl}
+    out['local_train_step'] = {'value': Bl * world / (ms / 1e3), 'unit': 'single patches/s', 'ms_per_step': ms, 'patches_per_gpu': Bl,
+                               'note': 'one kernel launch per step (setup, loss, backward, reduction fused); eager = Python + autograd glue bound'}
+    try:   # the same step captured in a CUDA graph (what a captured training loop pays for it)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            local_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        le.grad = None
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            lcrit(le, lny, lgt, lbd, lderi).backward()
+        out['local_train_step']['ms_per_step_cuda_graph'] = _timed(gr.replay, max(steps, 10), 3, dev, barrier, world)
+        del gr
+    except Exception as e:
+        out['local_train_step']['cuda_graph_error'] = str(e)[:100]
     del lcrit, le, lny, lgt, lbd, lderi
     # ---- configs[4]: densify 'w' ----
     Bw = 32

@@ -87,7 +87,7 @@ _SIGS = {
     'be_host_global_loss_begin': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_double), C.c_int64, C.c_int32, _P, _P]),
     'be_host_global_loss_end': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_ctx_last_train_timing': (C.c_int, [_P, C.POINTER(C.c_float)]),
-    'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, _P, _P, _P, _P]),
+    'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, C.c_int32, _P, _P, _P, _P]),
     'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P]),
 }

@@ -65,6 +65,7 @@ struct be_ctx {
     float* crec;        // [max_batch*L][BE_CREC]
     float* T;           // [max_batch][H][W][BE_TW]
     float* partials;    // [max_batch*Hp*runs][8]
+    float* lpart;       // local loss: [max_batch][8] partial sums + the ticket of its last-CTA reduction
     int same_gt;        // the last be_global_loss_stage1 call had img_gt == img_ny
     int train_B;        // pairs of the batch whose stage 1 ran last
     int train_parts;    // rows of `partials` the last loss-kernel launch(es) wrote
@@ -234,7 +235,7 @@ int be_ctx_destroy(be_ctx* c) {
     if (!c) return 0;
     cudaFree(c->table); cudaFree(c->acc); cudaFree(c->stage);
     cudaFree(c->st_est); cudaFree(c->st_img); cudaFree(c->st_out);
-    cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec);
+    cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec); cudaFree(c->lpart);
     cudaFree(c->ht_raw); cudaFree(c->ht_ny); cudaFree(c->ht_gt); cudaFree(c->ht_bd); cudaFree(c->ht_deri); cudaFree(c->ht_zg);
     cudaFree(c->ht_grad); cudaFree(c->ht_gdep); cudaFree(c->ht_scal);
     for (int i = 0; i < BE_TRAIN_EVENTS; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
@@ -685,33 +686,38 @@ int be_host_global_loss(be_ctx* c, const float* raw, const float* img_ny, const 
     return be_host_global_loss_end(c, B, gammas7, np_, cnt, terms7, loss1, grad, c->st_streams[1]);
 }
 
-int be_local_loss(be_ctx* c, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
-                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, float* dev_terms, float* dev_loss,
-                  float* dev_grad, void* stream) {
+int be_local_loss(be_ctx* c, float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
+                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, int32_t wrap_in_place, float* dev_terms,
+                  float* dev_loss, float* dev_grad, void* stream) {
     if (check_ctx(c)) return 1;
     if (B == 0) return 0;
     BE_REQUIRE(dev_est && dev_img_ny && dev_img_gt && dev_bndry_dist && dev_deri && dev_terms && dev_loss, "null pointer");
     const BeGeom& g = c->g;
     BE_REQUIRE(g.H == g.R && g.W == g.R, "be_local_loss needs a context whose image is one %dx%d patch (got %dx%d)", g.R, g.R, g.H, g.W);
     BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d exceeds max_batch=%d", B, c->cfg.max_batch);
-    if (ensure_train_ws(c)) return 1;
+    if (!c->lpart) {   // per-CTA partial sums + the ticket of the last-CTA reduction
+        BE_CUDA(cudaMalloc(&c->lpart, (size_t)c->cfg.max_batch * 8 * sizeof(float) + 16));
+        BE_CUDA(cudaMemset(c->lpart, 0, (size_t)c->cfg.max_batch * 8 * sizeof(float) + 16));
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    be_launch_setup(dev_est, BE_PARAMS_LOCALRAW10, B, c->cam, c->table, c->gtable, st);
     const double RR = (double)g.R * g.R, Ri2 = (double)(g.R - 2) * (g.R - 2), Np = (double)B;
     BeLossArgs a;
     memset(&a, 0, sizeof(a));
-    a.table = c->table; a.gtable = c->gtable; a.grad = dev_grad; a.partials = c->partials;
-    a.l_ny = dev_img_ny; a.l_gt = dev_img_gt; a.l_bd = dev_bndry_dist; a.l_deri = dev_deri;
+    a.grad = dev_grad; a.partials = c->lpart;
+    a.l_est = dev_est; a.l_ny = dev_img_ny; a.l_gt = dev_img_gt; a.l_bd = dev_bndry_dist; a.l_deri = dev_deri;
     a.g = g; a.NB = B; a.G = 1; a.runs_per_row = 1;
-    BeLossScale sc;
-    memset(&sc, 0, sizeof(sc));
-    sc.nterms = 3;                                        // loss = colour + beta_loc * loc + beta_smth * smth (local_training.py:47-52)
-    sc.src[0] = 0; sc.src[1] = 5; sc.src[2] = 3;
-    sc.scale[0] = 1.0 / (RR * Np); sc.scale[1] = 1.0 / (RR * Np); sc.scale[2] = 1.0 / (Ri2 * Np);
-    sc.gamma[0] = 1.0f; sc.gamma[1] = (float)beta_bndry_loc; sc.gamma[2] = (float)beta_smthns;
-    a.kc = (float)sc.scale[0]; a.kbl = (float)(beta_bndry_loc * sc.scale[1]); a.ks = (float)(beta_smthns * sc.scale[2]);
-    be_launch_loss(a, st);
-    be_launch_loss_reduce(c->partials, B, sc, nullptr, nullptr, 0.0, dev_terms, dev_loss, st);
+    BeLocalTail t;
+    memset(&t, 0, sizeof(t));
+    t.cam = c->cam;
+    t.sc.nterms = 3;                                       // loss = colour + beta_loc * loc + beta_smth * smth (local_training.py:47-52)
+    t.sc.src[0] = 0; t.sc.src[1] = 5; t.sc.src[2] = 3;
+    t.sc.scale[0] = 1.0 / (RR * Np); t.sc.scale[1] = 1.0 / (RR * Np); t.sc.scale[2] = 1.0 / (Ri2 * Np);
+    t.sc.gamma[0] = 1.0f; t.sc.gamma[1] = (float)beta_bndry_loc; t.sc.gamma[2] = (float)beta_smthns;
+    a.kc = (float)t.sc.scale[0]; a.kbl = (float)(beta_bndry_loc * t.sc.scale[1]); a.ks = (float)(beta_smthns * t.sc.scale[2]);
+    t.est_wrapped = wrap_in_place ? dev_est : nullptr;
+    t.ticket = reinterpret_cast<unsigned*>(c->lpart + (size_t)c->cfg.max_batch * 8);
+    t.terms = dev_terms; t.loss = dev_loss;
+    be_launch_loss(a, t, st);
     BE_CUDA(cudaGetLastError());
     return 0;
 }

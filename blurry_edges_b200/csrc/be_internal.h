@@ -59,6 +59,7 @@ struct BeLossArgs {
     const float* T;                   // packed targets of the global loss: 8 float4 planes + 1 scalar plane over [NB][H][W] (be_train.cu)
     int same_gt;                      // img_gt is img_ny (the training call, global_training.py:210): the loss kernel never touches the GT planes
     const float *l_ny, *l_gt, *l_bd, *l_deri;   // local loss: [NB,R,R,3], [NB,R,R,3], [NB,R,R], [NB,R-2,R-2,3]
+    const float* l_est;               // local loss: raw LocalStage output [NB,10]; the kernel builds the patch record itself (table may be null)
     float* grad;                      // [N][12|10] or nullptr
     float* grad_depth;                // [N][4] or nullptr: the depth term's share of the eta gradients, NOT divided by the mask count
                                       // (deferred normaliser: the count of the whole batch is still being all-reduced)
@@ -80,13 +81,22 @@ struct BeLossScale {                  // partial sums -> reported terms
     int masked[7];
 };
 
+struct BeLocalTail {                  // single-launch local loss: in-kernel setup + last-CTA reduction (be_train.cu)
+    BeCam cam;
+    BeLossScale sc;
+    float* est_wrapped;               // nullable: the angles of est are written back wrapped to [0, 2 pi) (local_training.py:33)
+    unsigned* ticket;                 // device counter, zero between launches
+    float* terms;
+    float* loss;
+};
+
 // launchers (be_kernels.cu / be_train.cu); all asynchronous on `st`
 void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, float* gtable, cudaStream_t st);
 // pairs [b0, b0 + nb) of whole-batch arrays laid out for Btot pairs
 void be_launch_train_normalise(const float* acc, const BeGeom& g, int b0, int nb, int Btot, float* T, float* gimg, float* gbnd, cudaStream_t st);
 void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt, const float* bndry_dist,
                           const float* deri, const float* bndry_depth, float* T, cudaStream_t st);
-void be_launch_loss(const BeLossArgs& a, cudaStream_t st);               // local-stage loss (be_train.cu)
+void be_launch_loss(const BeLossArgs& a, const BeLocalTail& tail, cudaStream_t st);   // local-stage loss, one launch (be_train.cu)
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
 void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, const unsigned long long* true_patches,
                                 double assumed_patches, size_t npatch, cudaStream_t st);

@@ -55,6 +55,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 
 // Read-only loads the compiler may not merge with an earlier load of the same address: when img_gt is img_ny, stage D re-reads
 // the values stage A has already used instead of keeping them in registers across the two stencil stages.
+// Diagnosis builds (results wrong on purpose; -DBE_LOSS2_DIAG=n via BE_NVCC_EXTRA): 1 = every patch of a run reads the first patch's
+// target window (L1 hits), 2 = no target loads at all, 3 = no stencil loads from shared memory, 4 = no stencil barriers.
+#ifndef BE_LOSS2_DIAG
+#define BE_LOSS2_DIAG 0
+#endif
+#if BE_LOSS2_DIAG == 2
+#define BE_TLD4(p) make_float4(0.25f, 0.5f, 0.75f, 0.125f)
+#define BE_TLD2(p) make_float2(0.25f, 0.5f)
+#define BE_TLD1(p) 0.9f
+#else
+#define BE_TLD4(p) __ldg(reinterpret_cast<const float4*>(p))
+#define BE_TLD2(p) __ldg(reinterpret_cast<const float2*>(p))
+#define BE_TLD1(p) __ldg(p)
+#endif
+#if BE_LOSS2_DIAG == 3
+#define BE_SLD4(p) make_float4(0.25f, 0.5f, 0.75f, 0.125f)
+#else
+#define BE_SLD4(p) (*(p))
+#endif
+
 __device__ __forceinline__ float4 ldg_again4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -307,7 +327,11 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
             C[8] = s_crec[cur][8];
         };
+#if BE_LOSS2_DIAG == 1
+        const unsigned tp[2] = {toff0[0] + 4u * (unsigned)(px0 * g.stride), toff0[1] + 4u * (unsigned)(px0 * g.stride)};
+#else
         const unsigned tp[2] = {toff0[0] + 4u * x0, toff0[1] + 4u * x0};      // element offset of plane 0 of each slot's pixel in the packed targets
+#endif
 
         // ---------------- stage A: distances, soft indicators, render, direct dL/dP ----------------
         f2 h[4], G[6];
@@ -321,14 +345,14 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (SAMEGT) {                            // gt = ny: values 0..5 (plane 0 and the first half of plane 1)
-                    t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
-                    t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
+                    t2[s] = BE_TLD4(a.T + tp[s]);
+                    t1[s] = BE_TLD2(a.T + (tp[s] + TPS));
                 } else {                                 // values 6..11 (second half of plane 1 and plane 2)
-                    t1[s] = __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS + 2u)));
-                    t2[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 2u * TPS)));
+                    t1[s] = BE_TLD2(a.T + (tp[s] + TPS + 2u));
+                    t2[s] = BE_TLD4(a.T + (tp[s] + 2u * TPS));
                 }
-                t3[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 3u * TPS)));
-                t4[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 4u * TPS)));
+                t3[s] = BE_TLD4(a.T + (tp[s] + 3u * TPS));
+                t4[s] = BE_TLD4(a.T + (tp[s] + 4u * TPS));
             }
             f2 d1, d2;
             be_pixel_dists2(P, X, Y, g.w, &d1, &d2);
@@ -372,16 +396,18 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             s_stash0[tid] = make_float4(lo(d1), hi(d1), lo(d2), hi(d2));
             s_stash1[tid] = make_float4(gb_[0], gb_[1], bd_[0], bd_[1]);
         }
+#if BE_LOSS2_DIAG != 4
         bar_sync_id<BAR_RENDER, NT>();   // (X1) rendered patch visible to the render warps
+#endif
 
         // ---------------- stage B: Sobel magnitude of the rendered patch, its loss and gradient (both slots packed) ----------------
         {
             float4 t6[2], t7[2], t8[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                t6[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 5u * TPS)));      // values 20..31: derivative targets
-                t7[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 6u * TPS)));
-                t8[s] = __ldg(reinterpret_cast<const float4*>(a.T + (tp[s] + 7u * TPS)));
+                t6[s] = BE_TLD4(a.T + (tp[s] + 5u * TPS));      // values 20..31: derivative targets
+                t7[s] = BE_TLD4(a.T + (tp[s] + 6u * TPS));
+                t8[s] = BE_TLD4(a.T + (tp[s] + 7u * TPS));
             }
             f2 ux[4], uy[4];                           // Sobel responses of (u1, u2) of image 1 and of image 2
 #pragma unroll
@@ -394,7 +420,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                     const float wx = (float)(((oi == 0) ? 2 : 1) * oj);       // sobel_x[oi+1][oj+1]
                     const float wy = (float)(-oi * ((oj == 0) ? 2 : 1));      // sobel_y[oi+1][oj+1]
                     const float4* pn = s_P2 + (tid + HALO + oi * R + oj);
-                    const float4 v0 = pn[0], v1 = pn[NE];
+                    const float4 v0 = BE_SLD4(pn), v1 = BE_SLD4(pn + NE);
                     const f2 uv[4] = {mk2(v0.x, v0.y), mk2(v0.z, v0.w), mk2(v1.x, v1.y), mk2(v1.z, v1.w)};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -467,7 +493,9 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             row[2] = make_float4(fold(sums[8]), 0.0f, 0.0f, 0.0f);
         }
         bar_arrive_id<BAR_ATG, NTHR>();  // A^T G partial sums handed to the helper
+#if BE_LOSS2_DIAG != 4
         bar_sync_id<BAR_RENDER, NT>();   // (X2) projected Sobel gradients visible
+#endif
 
         // ---------------- stage C: adjoint of the Sobel filter on the projected fields ----------------
         f2 AE[4];                                    // sum_c A_c (C_k - C_0)_c for (k = 1, 2) of image 1, then of image 2
@@ -482,12 +510,12 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 const float wy = (float)(di * ((dj == 0) ? 2 : 1));    // weight of gy(i+di, j+dj)
                 const float4* pn = s_G2 + (tid + HALO + di * R + dj);
                 if (wx != 0.0f) {
-                    const float4 v0 = pn[0], v1 = pn[NE];
+                    const float4 v0 = BE_SLD4(pn), v1 = BE_SLD4(pn + NE);
                     AE[0] = fma2(bc2(wx), mk2(v0.x, v0.y), AE[0]); AE[1] = fma2(bc2(wx), mk2(v0.z, v0.w), AE[1]);
                     AE[2] = fma2(bc2(wx), mk2(v1.x, v1.y), AE[2]); AE[3] = fma2(bc2(wx), mk2(v1.z, v1.w), AE[3]);
                 }
                 if (wy != 0.0f) {
-                    const float4 v0 = pn[2 * NE], v1 = pn[3 * NE];
+                    const float4 v0 = BE_SLD4(pn + 2 * NE), v1 = BE_SLD4(pn + 3 * NE);
                     AE[0] = fma2(bc2(wy), mk2(v0.x, v0.y), AE[0]); AE[1] = fma2(bc2(wy), mk2(v0.z, v0.w), AE[1]);
                     AE[2] = fma2(bc2(wy), mk2(v1.x, v1.y), AE[2]); AE[3] = fma2(bc2(wy), mk2(v1.z, v1.w), AE[3]);
                 }
@@ -503,10 +531,14 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             float zgv[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
+#if BE_LOSS2_DIAG == 2
+                const float4 q0 = BE_TLD4(a.T); const float2 q1 = BE_TLD2(a.T);
+#else
                 const float4 q0 = SAMEGT ? ldg_again4(a.T + tp[s]) : __ldg(reinterpret_cast<const float4*>(a.T + tp[s]));
                 const float2 q1 = SAMEGT ? ldg_again2(a.T + (tp[s] + TPS)) : __ldg(reinterpret_cast<const float2*>(a.T + (tp[s] + TPS)));
+#endif
                 ny[s][0] = q0.x; ny[s][1] = q0.y; ny[s][2] = q0.z; ny[s][3] = q0.w; ny[s][4] = q1.x; ny[s][5] = q1.y;
-                zgv[s] = __ldg(a.T + (8u * TPS + (tp[s] >> 2)));        // value 32: the scalar plane
+                zgv[s] = BE_TLD1(a.T + (8u * TPS + (tp[s] >> 2)));        // value 32: the scalar plane
             }
             const float4 sd = s_stash0[tid], sg = s_stash1[tid];
             const f2 d1 = mk2(sd.x, sd.y), d2 = mk2(sd.z, sd.w), gbv = mk2(sg.x, sg.y), bdv = mk2(sg.z, sg.w);

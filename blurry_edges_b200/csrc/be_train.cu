@@ -126,7 +126,11 @@ struct Slot {
     bool valid, interior;
 };
 
-__global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
+// Single launch for the whole step (local_training.py:99-108 calls it on 64 patches): the CTA builds its patch record itself
+// (a.l_est != nullptr: no be_setup_kernel launch, no table in HBM), and the last CTA to finish - an atomic ticket - adds the CTAs'
+// partial sums in fixed order and writes terms and loss (no be_loss_reduce_kernel launch).  One CTA per patch, at most a few hundred
+// CTAs: occupancy is irrelevant, so the kernel takes the registers it wants (no spills).
+__global__ void __launch_bounds__(BE_THREADS, 1) be_local_loss_kernel(const BeLossArgs a, const BeLocalTail tail) {
     constexpr int NIMG = 1;
     constexpr int NCH = 3 * NIMG;
     constexpr int RRMAX = BE_MAX_R * BE_MAX_R;
@@ -157,9 +161,35 @@ __global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
     const int np = 10;
 
     if (tid < R) s_axis[tid] = be_axis(tid, R);
-    if (tid < 8) reinterpret_cast<float4*>(s_rec[0])[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
-    if (tid >= 8 && tid < 8 + BE_GREC / 4)
-        reinterpret_cast<float4*>(s_grec[0])[tid - 8] = __ldg(reinterpret_cast<const float4*>(a.gtable + patch0 * BE_GREC) + (tid - 8));
+    if (a.l_est != nullptr) {          // raw LocalStage output -> record, in place of be_setup_kernel (one patch per CTA: n == 1)
+        if (tid == 0) {
+            float p[12];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) p[q] = (q < 10) ? __ldg(a.l_est + patch0 * 10 + q) : 0.0f;
+            BePatch P;
+            BePatchGrad G;
+            be_patch_setup(p, BE_PARAMS_LOCALRAW10, tail.cam, P);
+            be_patch_grad_setup(p, BE_PARAMS_LOCALRAW10, tail.cam, P, G);
+            float4* rec = reinterpret_cast<float4*>(s_rec[0]);
+            rec[0] = make_float4(P.sn[0], P.sn[1], P.sn[2], P.sn[3]);
+            rec[1] = make_float4(P.cs[0], P.cs[1], P.cs[2], P.cs[3]);
+            rec[2] = make_float4(P.vx[0], P.vx[1], P.vy[0], P.vy[1]);
+            rec[3] = make_float4(P.flip[0], P.flip[1], P.z[0], P.z[1]);
+            rec[4] = make_float4(P.inv_eta[0], P.inv_eta[1], P.inv_eta[2], P.inv_eta[3]);
+            float4* gr = reinterpret_cast<float4*>(s_grec[0]);
+            gr[0] = make_float4(G.deta_dcoef[0], G.deta_dcoef[1], G.deta_dcoef[2], G.deta_dcoef[3]);
+            gr[1] = make_float4(G.dz_deta[0], G.dz_deta[1], G.dz_deta[2], G.dz_deta[3]);
+            gr[2] = make_float4(G.xy_scale, G.ang_scale, 0.f, 0.f);
+            if (tail.est_wrapped != nullptr) {      // the reference wraps the angles of the network output in place (local_training.py:33)
+#pragma unroll
+                for (int q = 4; q < 8; ++q) tail.est_wrapped[patch0 * 10 + q] = be_wrap_2pi(p[q]);
+            }
+        }
+    } else {
+        if (tid < 8) reinterpret_cast<float4*>(s_rec[0])[tid] = __ldg(reinterpret_cast<const float4*>(a.table + patch0 * BE_REC) + tid);
+        if (tid >= 8 && tid < 8 + BE_GREC / 4)
+            reinterpret_cast<float4*>(s_grec[0])[tid - 8] = __ldg(reinterpret_cast<const float4*>(a.gtable + patch0 * BE_GREC) + (tid - 8));
+    }
 
     Slot sl[2];
 #pragma unroll
@@ -184,7 +214,7 @@ __global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
     for (int k = 0; k < n; ++k) {
         const int cur = k & 1;
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (warp == 0 && k + 1 < n) {
+        if (warp == 0 && k + 1 < n && a.l_est == nullptr) {
             if (lane < 8) nxt = __ldg(reinterpret_cast<const float4*>(a.table + (patch0 + k + 1) * BE_REC) + lane);
             else if (lane < 8 + BE_GREC / 4) nxt = __ldg(reinterpret_cast<const float4*>(a.gtable + (patch0 + k + 1) * BE_GREC) + (lane - 8));
         }
@@ -492,6 +522,35 @@ __global__ void __maxnreg__(128) be_local_loss_kernel(const BeLossArgs a) {
             a.partials[(size_t)blockIdx.x * 8 + tid] = t;
         }
     }
+    if (tail.ticket == nullptr) return;
+    // ---------------- last CTA: partial sums -> terms and loss (fixed order, fp64) ----------------
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp == 0) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int i = lane; i < (int)gridDim.x; i += 32)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) acc[t] += (double)__ldcg(a.partials + (size_t)i * 8 + tail.sc.src[t]);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc[t] += __shfl_xor_sync(FULL, acc[t], m);
+        if (lane == 0) {
+            double l = 0.0;
+            for (int t = 0; t < tail.sc.nterms; ++t) {
+                const double v = acc[t] * tail.sc.scale[t];
+                tail.terms[t] = (float)v;
+                l += (double)tail.sc.gamma[t] * v;
+            }
+            *tail.loss = (float)l;
+            *tail.ticket = 0u;                       // ready for the next launch
+        }
+    }
 }
 
 // partial sums -> terms (unweighted, as the oracle's `terms`) and the weighted loss
@@ -575,9 +634,9 @@ void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float
     ++g_be_launches;
 }
 
-void be_launch_loss(const BeLossArgs& a, cudaStream_t st) {
+void be_launch_loss(const BeLossArgs& a, const BeLocalTail& tail, cudaStream_t st) {
     const int grid = a.NB * a.g.Hp * a.runs_per_row;
-    be_local_loss_kernel<<<grid, BE_THREADS, 0, st>>>(a);
+    be_local_loss_kernel<<<grid, BE_THREADS, 0, st>>>(a, tail);
     ++g_be_launches;
 }
 

@@ -176,15 +176,19 @@ class LocalLossFused(nn.Module):
         if B > self.ctx.max_batch:
             self.ctx.close()
             self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
-        raw = self._f32(est.detach())
         want_grad = torch.is_grad_enabled() and est.requires_grad
+        det = est.detach()
+        # The reference mutates the network output (local_training.py:33: est[:, 4:8] = remainder(...)).  When est is a plain fp32
+        # CUDA tensor that autograd allows to be written (not a leaf that requires grad) the kernel wraps the angles in place itself.
+        in_place = det.is_cuda and det.dtype == torch.float32 and det.is_contiguous() and not (est.requires_grad and est.is_leaf)
+        raw = det if in_place else self._f32(det)
         ny = self._f32(img_ny)
         gt = ny if gt_img is img_ny else self._f32(gt_img)
         terms, loss, grad = self.ctx.local_loss(raw, ny, gt, self._f32(bndry_dist), self._f32(deri), self.beta_bndry_loc,
-                                                self.beta_smthns, want_grad)
+                                                self.beta_smthns, want_grad, wrap_in_place=in_place)
         self.terms = terms
-        with torch.no_grad():                                # the reference mutates the network output (local_training.py:33)
-            if not (est.requires_grad and est.is_leaf):
+        if not in_place and not (est.requires_grad and est.is_leaf):
+            with torch.no_grad():
                 est.data[:, 4:8] = torch.remainder(est.data[:, 4:8], 2 * torch.pi)
         if want_grad:
             return _FusedLossFn.apply(est, loss, grad.to(est.dtype))

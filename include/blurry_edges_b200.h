@@ -174,13 +174,14 @@ int be_host_global_loss_begin(be_ctx* ctx, const float* raw, const float* img_ny
 int be_host_global_loss_end(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
                             float* terms7, float* loss1, float* grad, void* stream);
 
-/* LocalLoss.forward + backward (local_training.py:32-52): est [B,10] raw LocalStage output (angles wrapped inside),
- * img_ny / img_gt [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation,
- * smoothness), loss [1] = terms[0] + beta_bndry_loc * terms[1] + beta_smthns * terms[2], grad [B,10] (may be NULL).
+/* LocalLoss.forward + backward (local_training.py:32-52) in ONE kernel launch: est [B,10] raw LocalStage output, img_ny / img_gt
+ * [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation, smoothness),
+ * loss [1] = terms[0] + beta_bndry_loc * terms[1] + beta_smthns * terms[2], grad [B,10] (may be NULL).  Like the reference (:33) the
+ * angles est[:, 4:8] are wrapped to [0, 2 pi) IN PLACE when wrap_in_place != 0 - the one input this library writes.
  * Needs a context created with H = W = R. */
-int be_local_loss(be_ctx* ctx, const float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
-                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, float* dev_terms, float* dev_loss,
-                  float* dev_grad, void* stream);
+int be_local_loss(be_ctx* ctx, float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
+                  const float* dev_deri, int32_t B, double beta_bndry_loc, double beta_smthns, int32_t wrap_in_place, float* dev_terms,
+                  float* dev_loss, float* dev_grad, void* stream);
 
 /* Method-granularity entry points: one per METHOD of PostProcessBase / PostProcessGlobalBase / DepthEtas, on the
  * reference's own tensor layouts, each with its backward (autograd of the reference).  Lsp = Hp*Wp for the global layout

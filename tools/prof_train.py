@@ -31,9 +31,11 @@ for _ in range(3):
     raw.grad = None
     crit(raw, img, gt, bd, deri, zg).backward()
 torch.cuda.synchronize()
+crit.ctx.set_timing(True)
 t0 = time.perf_counter()
 for _ in range(steps):
     raw.grad = None
     crit(raw, img, gt, bd, deri, zg).backward()
 torch.cuda.synchronize()
+print('kernel ms (memset, setup, run3<TRAINFWD>, normalise, pack, loss2, reduce):', ' '.join(f'{m:.4f}' for m in crit.ctx.last_train_timing()))
 print(f'B={B}{" same-gt" if same else ""}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms/step wall, {B * L * steps / (time.perf_counter() - t0) / 1e6:.1f} M patches/s')
