@@ -375,15 +375,17 @@ class Context:
                                                         _ptr(terms), _ptr(loss), _ptr(grad), _ptr(grad_depth), _stream(self.device)))
         return terms, loss, grad
 
-    def local_loss(self, est, img_ny, img_gt, bndry_dist, deri, beta_bndry_loc, beta_smthns, want_grad=True):
-        """-> (terms [3], loss [1], grad [B,10] | None)"""
+    def local_loss(self, est, img_ny, img_gt, bndry_dist, deri, beta_bndry_loc, beta_smthns, want_grad=True, wrap_in_place=False):
+        """-> (terms [3], loss [1], grad [B,10] | None); one kernel launch.  wrap_in_place: the angles est[:, 4:8] are written back
+        wrapped to [0, 2 pi), as the reference does to the network output (local_training.py:33)."""
         B, kw = est.shape[0], dict(device=self.device, dtype=torch.float32)
-        terms, loss = torch.empty(3, **kw), torch.empty(1, **kw)
+        out = torch.empty(4, **kw)
+        terms, loss = out[:3], out[3:]
         grad = torch.empty(B, 10, **kw) if want_grad else None
         with torch.cuda.device(self.device):
             check(self.lib.be_local_loss(self.h, _ptr(est), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri), B,
-                                         float(beta_bndry_loc), float(beta_smthns), _ptr(terms), _ptr(loss), _ptr(grad),
-                                         _stream(self.device)))
+                                         float(beta_bndry_loc), float(beta_smthns), int(wrap_in_place), C.c_void_p(terms.data_ptr()),
+                                         C.c_void_p(loss.data_ptr()), _ptr(grad), _stream(self.device)))
         return terms, loss, grad
 
     def host_global_loss(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, gammas, want_grad=True, out=None, process_group=None):
