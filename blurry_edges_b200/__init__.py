@@ -11,5 +11,6 @@ from .pipeline import DepthEstimatorFused
 from .losses import GlobalLossFused, LocalLossFused
 from .big import BigImageFused, block_windows, shard_blocks
 from .activations import SmishFused, patch_reference_smish, smish
+from .data import ShapePrefetcher
 
-__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'DepthEstimatorFused', 'block_windows', 'shard_blocks', 'SmishFused', 'patch_reference_smish', 'smish', '_lib']
+__all__ = ['DepthEtas', 'PostProcessBase', 'PostProcessGlobalBase', 'PostProcessLocalBase', 'BlurryEdgesError', 'Context', 'make_config', 'PostProcessFused', 'PostProcessLocalFused', 'GlobalLossFused', 'LocalLossFused', 'BigImageFused', 'DepthEstimatorFused', 'block_windows', 'shard_blocks', 'SmishFused', 'patch_reference_smish', 'smish', 'ShapePrefetcher', '_lib']

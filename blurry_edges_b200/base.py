@@ -82,12 +82,20 @@ class PostProcessBase(nn.Module, ABC):
     def get_adjA(self, A, A2, trA, trA2):
         pass
 
-    # compatibility helpers of the reference's own params2dists (:26-41); nothing in this package calls them
+    # Compatibility helpers of the reference's own params2dists (utils/postprocessing_loss.py:26-41): nothing in this package calls
+    # them (params2dists is one kernel), they exist for subclasses that do.  Both are one coordinate of the pixel grid expressed in
+    # the frame of an edge through (x, y) with direction `angle`.
+    def _edge_frame(self, x, y, angle):
+        """-> (normal coordinate, axial coordinate) of every pixel, differentiable torch ops"""
+        s, c = torch.sin(angle), torch.cos(angle)
+        dx, dy = self.x - x, self.y - y
+        return torch.addcmul(c * dy, s, dx, value=-1.0), torch.addcmul(c * dx, s, dy)
+
     def dist4edge(self, x, y, angle):
-        return -torch.sin(angle) * (self.x - x) + torch.cos(angle) * (self.y - y)
+        return self._edge_frame(x, y, angle)[0]
 
     def dist4axial(self, x, y, angle):
-        return torch.cos(angle) * (self.x - x) + torch.sin(angle) * (self.y - y)
+        return self._edge_frame(x, y, angle)[1]
 
     def itemize_params(self, params):
         return tuple(params[:, k, ...].unsqueeze(1).unsqueeze(1) for k in range(8))

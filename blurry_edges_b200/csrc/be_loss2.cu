@@ -448,10 +448,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 const f2 v = fma2(sx[c], sx[c], fma2(sy[c], sy[c], bc2(1e-8f)));
-                // v >= 1e-8: no denormal handling needed.  MUFU.RSQ (2 ulp) + one Newton step: the smoothness gradient sums 441
-                // signed terms per parameter that largely cancel, so the rounding of 1/|grad P| shows up in it (r2g: 1.6e-5 -> <1e-5)
-                f2 ir = mk2(be_rsqrt(lo(v)), be_rsqrt(hi(v)));
-                ir = mul2(ir, fma2(mul2(v, ir), mul2(ir, bc2(-0.5f)), bc2(1.5f)));
+                const f2 ir = mk2(be_rsqrt(lo(v)), be_rsqrt(hi(v)));          // v >= 1e-8: no denormal handling needed
                 const f2 mag = mul2(v, ir);
                 const f2 e1 = mk2(lo(mag) - dgt[0][c], hi(mag) - dgt[1][c]), e2 = mk2(lo(mag) - dgi[0][c], hi(mag) - dgi[1][c]);
                 l3 = fma2(e1, e1, l3);

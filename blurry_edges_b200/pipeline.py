@@ -36,6 +36,9 @@ class DepthEstimatorFused(nn.Module):
         key = (tuple(img_ny.shape), gt_depth is not None)
         entry = self._graphs.get(key)
         if entry is None:
+            # Captured graphs bake in the context's workspace pointers (patch table, accumulator): size the context for this batch
+            # BEFORE warm-up / capture, and throw away every graph captured against a context that is about to be replaced.
+            self._ensure_batch(img_ny.shape[0])
             s_img = torch.empty(tuple(img_ny.shape), device=self.device, dtype=torch.float32)
             s_gt = None if gt_depth is None else torch.empty(tuple(gt_depth.shape), device=self.device, dtype=torch.float32)
             s_img.copy_(img_ny)
@@ -58,11 +61,22 @@ class DepthEstimatorFused(nn.Module):
         graph.replay()
         return out
 
+    def _ensure_batch(self, B):
+        """Grow the context to B pairs.  A replaced context frees its workspace, so graphs captured against it are dropped (replaying
+        them would read and write freed device memory); growing inside a stream capture is refused."""
+        if B <= self.ctx.max_batch:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.BlurryEdgesError(f'batch of {B} pairs exceeds the context ({self.ctx.max_batch}) inside a CUDA-graph capture: '
+                                        'construct DepthEstimatorFused with max_batch >= the largest batch')
+        self._graphs.clear()
+        torch.cuda.synchronize(self.device)              # replays of the dropped graphs may still be in flight
+        self.ctx.close()
+        self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
+
     def _run(self, img_ny, gt_depth=None):
         B, H, W, R, L = img_ny.shape[0], self.H, self.W, self.R, self.L
-        if B > self.ctx.max_batch:
-            self.ctx.close()
-            self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
+        self._ensure_batch(B)
         planar = img_ny.to(device=self.device, dtype=torch.float32).permute(0, 1, 4, 2, 3).contiguous()      # [B,2,3,H,W]
         vec = torch.empty(2 * B * L, 3, R, R, device=self.device, dtype=torch.float32)
         self.ctx.call('be_patch_gather', planar, 2 * B, vec)                                                  # :119-121

@@ -182,3 +182,24 @@ def test_script_level_subclass_composed_from_methods():
     tol = {'image': 2e-5, 'sharp': 5e-5, 'refoc': 2e-5, 'bndry': 1e-5, 'depth': 1e-5, 'conf': 1e-6}    # bmm in fp32 on top of the kernels
     for name, r, o in zip(MAPS, ref, maps):
         assert relmax(o.cpu().numpy(), r.numpy()) < tol[name], name
+
+
+def test_edge_frame_helpers_match_the_reference_formulas(gbase, lbase):
+    """dist4edge / dist4axial / itemize_params (utils/postprocessing_loss.py:26-41): d = -sin a (X - x) + cos a (Y - y),
+    t = cos a (X - x) + sin a (Y - y) on the pixel grid, in both broadcasting layouts."""
+    g = geom(45)
+    p = _geo_global(2, g.Hp, 5).cuda()
+    x0, y0, _, _, a0, _, _, _ = gbase.itemize_params(p)
+    ax = O.pixel_axis(21, F64)
+    X, Y = ax.view(1, 1, 21, 1, 1), ax.view(1, 21, 1, 1, 1)
+    xs, ys, an = [t.cpu().to(F64) for t in (x0, y0, a0)]
+    d_ref = -torch.sin(an) * (X - xs) + torch.cos(an) * (Y - ys)
+    t_ref = torch.cos(an) * (X - xs) + torch.sin(an) * (Y - ys)
+    assert relmax(gbase.dist4edge(x0, y0, a0).cpu().numpy(), d_ref.numpy()) < 1e-6
+    assert relmax(gbase.dist4axial(x0, y0, a0).cpu().numpy(), t_ref.numpy()) < 1e-6
+    pl = O.restore_global(synth.raw_global(1, 6, seed=9))[0, :, :8].contiguous().cuda()
+    xl, yl, _, _, al, _, _, _ = lbase.itemize_params(pl)
+    dl = lbase.dist4edge(xl, yl, al)
+    assert dl.shape == (6, 21, 21)
+    ref = -torch.sin(al.cpu().to(F64)) * (ax.view(1, 1, 21) - xl.cpu().to(F64)) + torch.cos(al.cpu().to(F64)) * (ax.view(1, 21, 1) - yl.cpu().to(F64))
+    assert relmax(dl.cpu().numpy(), ref.numpy()) < 1e-6

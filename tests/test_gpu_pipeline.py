@@ -122,3 +122,26 @@ def test_driver_body_as_cuda_graph_equals_eager():
     te, tg = lat(eager), lat(graphed)
     print(f'driver body, 1 pair {S}x{S}, stand-in networks: eager {te * 1e6:.0f} us, CUDA graph {tg * 1e6:.0f} us')
     assert tg < te
+
+
+def test_cuda_graphs_are_dropped_when_the_context_is_regrown():
+    """a captured graph bakes in the context's workspace pointers; a larger batch replaces the context and frees them.
+    Graphs captured before must not be replayed afterwards: B=1 (capture), B=3 (context regrown, new capture), B=1 again (captured
+    anew, against the live context) - every result equals the eager driver."""
+    from blurry_edges_b200 import DepthEstimatorFused
+    S = GEOMS['mid']
+    args = argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[S, S], batch_size=1, mag=4.0, rho_prime=10.39,
+                              densify=None, crop=10, cam_params=CAMP)
+    local_m, global_m = TinyLocal().cuda(), TinyGlobal().cuda()
+    eager = DepthEstimatorFused(args, local_m, global_m, 'cuda:0', max_batch=3)
+    graphed = DepthEstimatorFused(args, local_m, global_m, 'cuda:0', cuda_graph=True)       # context sized for ONE pair
+    for step, B in enumerate((1, 3, 1, 3)):
+        img = synth.image_pairs(B, S, S, seed=120 + step).cuda()
+        before = graphed.ctx
+        b = {k: v.clone() for k, v in graphed(img).items()}
+        if step == 1:
+            assert graphed.ctx is not before and len(graphed._graphs) == 1                  # the B=1 graph went with the old context
+        a = eager(img)
+        torch.cuda.synchronize()
+        for k in a:
+            assert relmax(b[k].cpu().numpy(), a[k].cpu().numpy()) < 2e-6, (step, k)

@@ -64,7 +64,9 @@ def _metrics(stdout):
     avg = re.findall(r'Average metrics for whole dataset: (.*)', stdout)
     assert per and avg, stdout[-800:]
     nums = lambda line: [float(v) for v in re.findall(r'=\s*([0-9.]+)', line)]
-    return dict(per_pair=per, average=avg[0], values=np.array([nums(l) for l in per]))
+    # "--- Running time: x s" is the script's own stopwatch around one pair (blurry_edges_test.py:117,145-146); the first pair warms up
+    rt = [float(v) for v in re.findall(r'--- Running time:\s*([0-9.]+) s', stdout)]
+    return dict(per_pair=per, average=avg[0], values=np.array([nums(l) for l in per]), script_seconds_per_pair=rt)
 
 
 def _close(a, b):
@@ -91,7 +93,8 @@ def test_blurry_edges_test_py(assets, densify, tmp_path):
         if mode == 'fused':
             assert "('PostProcess', 'PostProcessFused')" in err
     key = f'blurry_edges_test.py{" --densify w" if densify else ""}'
-    SUMMARY[key] = {m: dict(per_pair=v['per_pair'], average=v['average'], seconds=v['seconds']) for m, v in got.items()}
+    SUMMARY[key] = {m: dict(per_pair=v['per_pair'], average=v['average'], seconds=v['seconds'],
+                            script_stopwatch_seconds_per_pair=v['script_seconds_per_pair']) for m, v in got.items()}
     for mode in modes[1:]:
         ok, dd, dr = _close(got[mode]['values'], got['cuda']['values'])
         SUMMARY[key][mode]['max_abs_diff_of_deltas_vs_reference_classes_on_gpu'] = dd
@@ -264,3 +267,52 @@ def test_fresh_transformer_output_vs_reference_classes_in_fp64():
     SUMMARY['GlobalLoss on a freshly initialised GlobalStage output: reference classes fp64 / fp32 vs GlobalLossFused'] = rec
     if saved_utils is not None:
         sys.modules['utils'] = saved_utils
+
+
+def test_real_networks_driver_body_eager_vs_cuda_graph(assets):
+    """the whole inference driver body (blurry_edges_test.py:114-149) with the REAL LocalStage CNN and GlobalStage
+    transformer of the reference (random-init weights of tools/make_assets.py) inside DepthEstimatorFused, eager and captured in ONE CUDA
+    graph (gather -> LocalStage -> pass A -> pm -> GlobalStage -> pass B -> metrics).  Outputs must agree; the per-pair latencies go to
+    the summary next to the unmodified script's own stopwatch."""
+    import argparse
+    import importlib
+    for p in (os.path.join(ROOT, 'tests', '_stubs'), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    models = importlib.import_module('models')
+    from blurry_edges_b200 import DepthEstimatorFused
+    dev = torch.device('cuda:0')
+    local_m = models.LocalStage().to(dev)
+    local_m.load_state_dict(torch.load(f'{assets}/weights/pretrained_local_stage.pth'))
+    global_m = models.GlobalStage(in_parameter_size=38, out_parameter_size=12, device=dev).to(dev)
+    global_m.load_state_dict(torch.load(f'{assets}/weights/pretrained_global_stage.pth'))
+    local_m.eval(); global_m.eval()
+    args = argparse.Namespace(R=21, stride=2, w=1.0, alpha_lambda=5e-3, img_size=[147, 147], batch_size=1, mag=4.0, rho_prime=10.39, densify=None,
+                              crop=10, cam_params={'s': 0.1104, 'rho_1': 10.0, 'rho_2': 10.2, 'sigma_cam': 0.003, 'pixel_pitch': 5.86e-6})
+    ny = torch.from_numpy(np.load(f'{assets}/eval/images_ny.npy')).float()
+    alpha = torch.from_numpy(np.load(f'{assets}/eval/alphas.npy')).float()
+    gt = torch.from_numpy(np.load(f'{assets}/eval/depth_maps.npy')).float().to(dev)
+    img = (ny / alpha.view(-1, 1, 1, 1, 1)).to(dev)
+    eager = DepthEstimatorFused(args, local_m, global_m, dev)
+    graphed = DepthEstimatorFused(args, local_m, global_m, dev, cuda_graph=True)
+    worst = 0.0
+    for b in range(2):
+        a = eager(img[b:b + 1], gt[b:b + 1])
+        g_ = graphed(img[b:b + 1], gt[b:b + 1])
+        torch.cuda.synchronize()
+        for k in a:
+            e = float((a[k] - g_[k]).abs().max() / a[k].abs().max().clamp_min(1e-30))
+            worst = max(worst, e)
+    def lat(m):
+        for _ in range(3):
+            m(img[:1], gt[:1])
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(10):
+            m(img[:1], gt[:1])
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 10
+    te, tg = lat(eager), lat(graphed)
+    SUMMARY['driver body with the real LocalStage / GlobalStage (DepthEstimatorFused, 1 pair 147x147)'] = dict(
+        eager_ms_per_pair=te * 1e3, cuda_graph_ms_per_pair=tg * 1e3, max_rel_diff_graph_vs_eager=worst,
+        metrics_of_pair_0=[float(v) for v in eager(img[:1], gt[:1])['metrics'][0]])
+    assert worst < 1e-4 and tg <= te * 1.05, (worst, te, tg)
