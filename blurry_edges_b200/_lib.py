@@ -80,6 +80,8 @@ _SIGS = {
     'be_assemble_pm': (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     'be_eval_depth': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     'be_global_loss_stage1': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    'be_global_loss_stage1_render': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
+    'be_global_loss_stage1_targets': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     'be_global_loss_stage2': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
     'be_global_loss_stage2_launch': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P]),
     'be_global_loss_stage2_finish': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
@@ -306,24 +308,34 @@ class Context:
                                                  _stream(self.device)))
         return acc
 
-    def fold_normalise(self, acc, thres, y0=0, full_H=None):
+    def fold_normalise(self, acc, thres, y0=0, full_H=None, packed=False):
         """acc [B,rows,accW,16] holding image rows [y0, y0 + rows) of full_H (default: the whole image) ->
-        (image, sharp, refoc, bndry, depth, conf, depth_thresholded) for those rows"""
+        (image, sharp, refoc, bndry, depth, conf, depth_thresholded) for those rows.  packed=True (B = 1): the seven maps are
+        consecutive plane ranges of ONE [16, rows, W] tensor, returned as an eighth element (one message per rank in the band gather)."""
         B, H, W = acc.shape[0], acc.shape[1], acc.shape[2]
         full_H = H if full_H is None else int(full_H)
         kw = dict(device=self.device, dtype=torch.float32)
-        out = [torch.empty(B, 2, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw),
-               torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
+        if packed:
+            if B != 1:
+                raise BlurryEdgesError('packed outputs need a single image')
+            buf = torch.empty(16, H, W, **kw)
+            out = [buf[0:6].view(1, 2, 3, H, W), buf[6:9].view(1, 3, H, W), buf[9:12].view(1, 3, H, W), buf[12:13].view(1, 1, H, W),
+                   buf[13:14].view(1, H, W), buf[14:15].view(1, H, W), buf[15:16].view(1, H, W)]
+        else:
+            out = [torch.empty(B, 2, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw), torch.empty(B, 3, H, W, **kw),
+                   torch.empty(B, 1, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw), torch.empty(B, H, W, **kw)]
         if H > 0:
             with torch.cuda.device(self.device):
                 check(self.lib.be_fold_normalise_band(self.h, _ptr(acc), B, int(y0), H, full_H, W, float(thres), *[_ptr(t) for t in out],
                                                       _stream(self.device)))
-        return out
+        return out + [buf] if packed else out
 
     # ---- training entry points -----------------------------------------------------------
-    def global_loss_stage1(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, want_maps=True):
+    def global_loss_stage1(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, want_maps=True, between=None):
         """-> (global_image [B,2,3,H,W] | None, global_bndry [B,1,H,W] | None, counts int64[2] = (mask count, B*L): the pair a
-        data-parallel caller all-reduces in one 16-byte collective)"""
+        data-parallel caller all-reduces in one 16-byte collective).  `between(counts)`: called after the render kernels (the count
+        is final once they finish) and before the target kernels are launched - where a data-parallel caller starts its all-reduce;
+        its return value is handed back as a fourth element."""
         B, H, W, kw = raw.shape[0], self.cfg.H, self.cfg.W, dict(device=self.device, dtype=torch.float32)
         gimg = torch.empty(B, 2, 3, H, W, **kw) if want_maps else None
         gbnd = torch.empty(B, 1, H, W, **kw) if want_maps else None
@@ -331,14 +343,18 @@ class Context:
         if tmpl is None or tmpl[0] != B:
             tmpl = self._cnt_template = (B, torch.tensor([0, B * self.L], dtype=torch.int64).to(self.device))
         cnt = tmpl[1].clone()
-        with torch.cuda.device(self.device):
-            check(self.lib.be_global_loss_stage1(self.h, _ptr(raw), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri),
-                                                 _ptr(bndry_depth), B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()),
-                                                 _stream(self.device)))
+        ptrs = (_ptr(raw), _ptr(img_ny), _ptr(img_gt), _ptr(bndry_dist), _ptr(deri), _ptr(bndry_depth))
         # the C side compares the two device pointers the same way (be_global_loss_stage1): the training call of the reference
         # passes one tensor twice (global_training.py:210) and gets the kernel variant that skips the GT target planes
         self.last_same_gt = img_ny.data_ptr() == img_gt.data_ptr()
-        return gimg, gbnd, cnt
+        with torch.cuda.device(self.device):
+            if between is None:
+                check(self.lib.be_global_loss_stage1(self.h, *ptrs, B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()), _stream(self.device)))
+                return gimg, gbnd, cnt
+            check(self.lib.be_global_loss_stage1_render(self.h, *ptrs, B, C.c_void_p(cnt.data_ptr()), _stream(self.device)))
+            mid = between(cnt)
+            check(self.lib.be_global_loss_stage1_targets(self.h, *ptrs, B, _ptr(gimg), _ptr(gbnd), C.c_void_p(cnt.data_ptr()), _stream(self.device)))
+        return gimg, gbnd, cnt, mid
 
     def global_loss_stage2(self, B, gammas, global_patches, mask_count, want_grad=True):
         """-> (terms [7], loss [1], grad [B,L,12] | None)"""

@@ -117,10 +117,10 @@ class BigImageFused(nn.Module):
             self.ctx.render_fold_blocks(est, img, _lib.planar_layout(self.big_H, self.big_W), blocks, acc, acc_y0=a)
         return acc
 
-    def finish(self, acc, thres=0.05, y0=0):
+    def finish(self, acc, thres=0.05, y0=0, packed=False):
         """accumulator (rows [y0, y0 + acc rows) of the image) -> (col_est [1,2,3,rows,W], col_shpd, col_refoc, bndry_est, depth,
-        confidence, thresholded depth) for those rows."""
-        return tuple(self.ctx.fold_normalise(acc, thres, y0=y0, full_H=self.big_H))
+        confidence, thresholded depth) for those rows (packed=True: plus the [16,rows,W] tensor they are views of)."""
+        return tuple(self.ctx.fold_normalise(acc, thres, y0=y0, full_H=self.big_H, packed=packed))
 
     def forward(self, est, big_img, thres=0.05, gather=True):
         """All blocks on this device; with a process_group: est holds this rank's band of blocks (see shard_blocks).  The ranks
@@ -139,8 +139,12 @@ class BigImageFused(nn.Module):
         rows = (min(span[0], bands[rank][0]), max(span[1], bands[rank][1]))      # one accumulator over the rows written and the rows owned
         part = self.render_partial(est, big_img, lo, hi, rows=rows)
         band = exchange_row_bands(part[0], rows, span, spans, bands, self.process_group)
-        maps = self.finish(band.unsqueeze(0), thres, y0=bands[rank][0])
+        maps = self.finish(band.unsqueeze(0), thres, y0=bands[rank][0], packed=True)
         if not gather:
-            return maps, bands[rank]
-        out = gather_row_bands(maps, bands, group=self.process_group)
-        return tuple(out) if out is not None else None
+            return maps[:7], bands[rank]
+        full = gather_row_bands(maps[7], bands, group=self.process_group)          # [16,H,W] on rank 0
+        if full is None:
+            return None
+        H, W = self.big_H, self.big_W
+        return (full[0:6].view(1, 2, 3, H, W), full[6:9].view(1, 3, H, W), full[9:12].view(1, 3, H, W), full[12:13].view(1, 1, H, W),
+                full[13:14].view(1, H, W), full[14:15].view(1, H, W), full[15:16].view(1, H, W))

@@ -396,44 +396,49 @@ static int ensure_train_events(be_ctx* c) {
 // flight at the same time (every workspace array is indexed by pair).
 static int loss_stage1_range(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,
                              const float* dev_deri, const float* dev_bndry_depth, int b0, int nb, int Btot, float* dev_global_image,
-                             float* dev_global_bndry, int64_t* dev_mask_count, cudaStream_t st, bool tm) {
+                             float* dev_global_bndry, int64_t* dev_mask_count, cudaStream_t st, bool tm, int parts = 3) {
     const BeGeom& g = c->g;
     const int L = g.Hp * g.Wp;
     const size_t HW = (size_t)g.H * g.W;
     const bool det = c->deterministic != 0;
-    if (det && ensure_stage(c, 8)) return 1;
-    if (tm) cudaEventRecord(c->tev[0], st);
-    if (!det) BE_CUDA(cudaMemsetAsync(c->acc + (size_t)b0 * HW * 8, 0, (size_t)nb * HW * 8 * sizeof(float), st));
-    if (tm) cudaEventRecord(c->tev[1], st);
-    be_launch_setup(dev_raw + (size_t)b0 * L * 12, BE_PARAMS_RAW12, nb * L, c->cam, c->table + (size_t)b0 * L * BE_REC,
-                    c->gtable + (size_t)b0 * L * BE_GREC, st);
-    if (tm) cudaEventRecord(c->tev[2], st);
-    BeRunArgs a;
-    memset(&a, 0, sizeof(a));
-    a.table = c->table + (size_t)b0 * L * BE_REC; a.acc = c->acc + (size_t)b0 * HW * 8;
-    a.img.p = dev_img_ny + (size_t)b0 * 6 * HW; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
-    a.zgt = dev_bndry_depth + (size_t)b0 * HW; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
-    a.crec = c->crec + (size_t)b0 * L * BE_CREC;
-    a.g = g; a.cam = c->cam; a.NB = nb; a.accH = g.H; a.accW = g.W;
-    pick_runs(g, nb, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
-    if (det) {
-        a.G = g.Wp; a.runs_per_row = 1;
-        a.stage = c->stage + (size_t)b0 * g.Hp * g.R * g.W * 8;
+    if (parts & 1) {   // render: records, TRAINFWD render + fold; the mask count is final when this part is done
+        if (det && ensure_stage(c, 8)) return 1;
+        if (tm) cudaEventRecord(c->tev[0], st);
+        if (!det) BE_CUDA(cudaMemsetAsync(c->acc + (size_t)b0 * HW * 8, 0, (size_t)nb * HW * 8 * sizeof(float), st));
+        if (tm) cudaEventRecord(c->tev[1], st);
+        be_launch_setup(dev_raw + (size_t)b0 * L * 12, BE_PARAMS_RAW12, nb * L, c->cam, c->table + (size_t)b0 * L * BE_REC,
+                        c->gtable + (size_t)b0 * L * BE_GREC, st);
+        if (tm) cudaEventRecord(c->tev[2], st);
+        BeRunArgs a;
+        memset(&a, 0, sizeof(a));
+        a.table = c->table + (size_t)b0 * L * BE_REC; a.acc = c->acc + (size_t)b0 * HW * 8;
+        a.img.p = dev_img_ny + (size_t)b0 * 6 * HW; a.img.sb = 6 * HW; a.img.sm = 3 * HW; a.img.sc = 1; a.img.sy = 3 * g.W; a.img.sx = 3;   // [B,2,H,W,3]
+        a.zgt = dev_bndry_depth + (size_t)b0 * HW; a.mask_count = reinterpret_cast<unsigned long long*>(dev_mask_count);
+        a.crec = c->crec + (size_t)b0 * L * BE_CREC;
+        a.g = g; a.cam = c->cam; a.NB = nb; a.accH = g.H; a.accW = g.W;
+        pick_runs(g, nb, RUN_CTAS, RUN_OVH, &a.G, &a.runs_per_row);
+        if (det) {
+            a.G = g.Wp; a.runs_per_row = 1;
+            a.stage = c->stage + (size_t)b0 * g.Hp * g.R * g.W * 8;
+        }
+        launch_run(BE_RUN_TRAINFWD, a, st);
+        if (tm) cudaEventRecord(c->tev[3], st);
+        if (det) be_launch_stage_reduce(a.stage, g, nb, 8, c->acc + (size_t)b0 * HW * 8, st);
     }
-    launch_run(BE_RUN_TRAINFWD, a, st);
-    if (tm) cudaEventRecord(c->tev[3], st);
-    if (det) be_launch_stage_reduce(a.stage, g, nb, 8, c->acc + (size_t)b0 * HW * 8, st);
-    be_launch_train_normalise(c->acc, g, b0, nb, Btot, c->T, dev_global_image, dev_global_bndry, st);
-    if (tm) cudaEventRecord(c->tev[4], st);
-    be_launch_train_pack(g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
-    if (tm) cudaEventRecord(c->tev[5], st);
+    if (parts & 2) {   // targets: global maps + packed per-pixel targets of the loss kernel
+        if (tm && !(parts & 1)) cudaEventRecord(c->tev[3], st);
+        be_launch_train_normalise(c->acc, g, b0, nb, Btot, c->T, dev_global_image, dev_global_bndry, st);
+        if (tm) cudaEventRecord(c->tev[4], st);
+        be_launch_train_pack(g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
+        if (tm) cudaEventRecord(c->tev[5], st);
+    }
     BE_CUDA(cudaGetLastError());
     return 0;
 }
 
-int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
-                          const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
-                          float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream) {
+static int global_loss_stage1_parts(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                                    const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                                    float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream, int parts) {
     if (check_ctx(c)) return 1;
     if (B == 0) return 0;
     BE_REQUIRE(dev_raw && dev_img_ny && dev_img_gt && dev_bndry_dist && dev_deri && dev_bndry_depth && dev_mask_count, "null pointer");
@@ -441,11 +446,36 @@ int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_
     if (ensure_train_ws(c)) return 1;
     if (c->timing && ensure_train_events(c)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), st));
-    c->same_gt = (dev_img_gt == dev_img_ny);
-    c->train_B = B;
+    if (parts & 1) {
+        BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), st));
+        c->same_gt = (dev_img_gt == dev_img_ny);
+        c->train_B = B;
+    } else {
+        BE_REQUIRE(c->train_B == B, "be_global_loss_stage1_render must run first on the same batch");
+    }
     return loss_stage1_range(c, dev_raw, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, 0, B, B, dev_global_image,
-                             dev_global_bndry, dev_mask_count, st, c->timing != 0);
+                             dev_global_bndry, dev_mask_count, st, c->timing != 0, parts);
+}
+
+int be_global_loss_stage1(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                          const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                          float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream) {
+    return global_loss_stage1_parts(c, dev_raw, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, B, dev_global_image,
+                                    dev_global_bndry, dev_mask_count, stream, 3);
+}
+
+int be_global_loss_stage1_render(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                                 const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                                 int64_t* dev_mask_count, void* stream) {
+    return global_loss_stage1_parts(c, dev_raw, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, B, nullptr, nullptr,
+                                    dev_mask_count, stream, 1);
+}
+
+int be_global_loss_stage1_targets(be_ctx* c, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                                  const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                                  float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream) {
+    return global_loss_stage1_parts(c, dev_raw, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, B, dev_global_image,
+                                    dev_global_bndry, dev_mask_count, stream, 2);
 }
 
 struct LossScales {

@@ -73,36 +73,22 @@ def exchange_row_bands(acc: torch.Tensor, acc_rows, span, spans, bands, group=No
     return acc[y0b - r0:y1b - r0]
 
 
-def gather_row_bands(maps, bands, out=None, group=None, dst_group_rank: int = 0):
-    """The finished maps of every rank's band ([..., band rows, W] tensors) -> full-height maps on one rank (None elsewhere).  Every
-    (plane, band) is a contiguous run of rows of the destination plane, so the bands are received straight into place with one
-    grouped batch of point-to-point transfers: no packing, no concatenation."""
+def gather_row_bands(packed: torch.Tensor, bands, group=None, dst_group_rank: int = 0):
+    """packed [P, band rows, W]: the finished planes of this rank's band -> [P, H, W] on one rank (None elsewhere).  ONE gather of
+    one message per rank (bands padded to the tallest), then one concatenation that drops the padding."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    W = maps[0].shape[-1]
-    H = bands[-1][1]
-    planes = [m.reshape(-1, m.shape[-2], W) for m in maps]
-    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-    ops = []
-    if rank == dst_group_rank:
-        if out is None:
-            out = [torch.empty(tuple(m.shape[:-2]) + (H, W), dtype=m.dtype, device=m.device) for m in maps]
-        full = [o.view(-1, H, W) for o in out]
-        for s, (y0, y1) in enumerate(bands):
-            for f, p in zip(full, planes):
-                for k in range(f.shape[0]):
-                    if s == rank:
-                        f[k, y0:y1].copy_(p[k])
-                    elif y1 > y0:
-                        ops.append(dist.P2POp(dist.irecv, f[k, y0:y1], glob(s), group))
-    else:
-        for p in planes:
-            for k in range(p.shape[0]):
-                if p.shape[1] > 0:
-                    ops.append(dist.P2POp(dist.isend, p[k], glob(dst_group_rank), group))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return out if rank == dst_group_rank else None
+    hmax = max(y1 - y0 for y0, y1 in bands)
+    P, rows, W = packed.shape
+    if rows != hmax:
+        pad = packed.new_empty(P, hmax, W)
+        pad[:, :rows] = packed
+        packed = pad
+    dst = dist.get_global_rank(group, dst_group_rank) if group is not None else dst_group_rank
+    lst = [torch.empty_like(packed) for _ in range(world)] if rank == dst_group_rank else None
+    dist.gather(packed.contiguous(), lst, dst=dst, group=group)
+    if rank != dst_group_rank:
+        return None
+    return torch.cat([t[:, :y1 - y0] for t, (y0, y1) in zip(lst, bands)], 1)
 
 
 def bind_to_gpu_numa_node(device_index: int) -> dict:

@@ -140,6 +140,15 @@ int be_fold_normalise_band(be_ctx* ctx, const float* dev_acc, int32_t B, int32_t
 int be_global_loss_stage1(be_ctx* ctx, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
                           const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
                           float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream);
+/* Stage 1 in two calls (same arguments): `render` ends with the kernel that counts the depth mask, `targets` builds the global maps
+ * and the packed targets.  A data-parallel caller starts the all-reduce of the count between the two: the collective's kernel then
+ * becomes resident while the small target kernels run, instead of queueing behind the loss kernel, which fills every SM. */
+int be_global_loss_stage1_render(be_ctx* ctx, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                                 const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                                 int64_t* dev_mask_count, void* stream);
+int be_global_loss_stage1_targets(be_ctx* ctx, const float* dev_raw, const float* dev_img_ny, const float* dev_img_gt,
+                                  const float* dev_bndry_dist, const float* dev_deri, const float* dev_bndry_depth, int32_t B,
+                                  float* dev_global_image, float* dev_global_bndry, int64_t* dev_mask_count, void* stream);
 int be_global_loss_stage2(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
                           float* dev_terms, float* dev_loss, float* dev_grad, void* stream);
 /* Stage 2 in two calls, for data-parallel callers: `launch` starts the loss kernel without the mask count (the depth term's share

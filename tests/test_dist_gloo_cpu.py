@@ -95,12 +95,12 @@ def _big_worker(rank, world, port, out):
     n = O.cover_count(O.Geometry(H=big, W=big), F64)[y0:y1]
     ok = torch.allclose(band[:, :, :3].permute(2, 0, 1) / n, ref[0][0, 0][:, y0:y1], rtol=0, atol=1e-10) and \
         torch.allclose(band[:, :, 3] / n, ref[3][0, 0][y0:y1], rtol=0, atol=1e-10)
-    # the finished bands are received straight into place on rank 0 (one grouped batch of point-to-point transfers)
+    # the finished bands go to rank 0 in one gather (one message per rank)
     from blurry_edges_b200.dist_utils import gather_row_bands
-    mine = [(band[:, :, :3].permute(2, 0, 1) / n).unsqueeze(0).contiguous(), (band[:, :, 3] / n).contiguous()]
+    mine = torch.cat([band[:, :, :3].permute(2, 0, 1) / n, (band[:, :, 3] / n).unsqueeze(0)]).contiguous()      # [4 planes, band rows, W]
     full = gather_row_bands(mine, bands)
     if rank == 0:
-        ok = ok and torch.allclose(full[0][0], ref[0][0, 0], rtol=0, atol=1e-10) and torch.allclose(full[1], ref[3][0, 0], rtol=0, atol=1e-10)
+        ok = ok and torch.allclose(full[:3], ref[0][0, 0], rtol=0, atol=1e-10) and torch.allclose(full[3], ref[3][0, 0], rtol=0, atol=1e-10)
     else:
         ok = ok and full is None
     out[rank] = bool(ok)
