@@ -87,8 +87,9 @@ _SIGS = {
     'be_global_loss_stage2_finish': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     'be_host_global_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_double), _P, _P, _P]),
     'be_host_global_loss_begin': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_double), C.c_int64, C.c_int32, _P, _P]),
-    'be_host_global_loss_end': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P]),
+    'be_host_global_loss_end': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_double), C.c_int64, _P, _P, _P, _P, _P, _P]),
     'be_ctx_last_train_timing': (C.c_int, [_P, C.POINTER(C.c_float)]),
+    'be_ctx_train_timing_at': (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
     'be_local_loss': (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_double, C.c_double, C.c_int32, _P, _P, _P, _P]),
     'be_host_render_fold': (C.c_int, [_P, _P, C.c_int32, _P, C.POINTER(BeImageLayout), C.c_int32, C.c_int32,
                                       _P, _P, _P, _P, _P, _P, _P]),
@@ -224,12 +225,12 @@ class Context:
             check(self.lib.be_ctx_last_timing(self.h, ms))
         return list(ms)
 
-    def last_train_timing(self):
+    def last_train_timing(self, steps_back=0):
         """ms of (memset, setup, be_run3_kernel<TRAINFWD>, train normalise, train pack, be_loss2_kernel, reduce + depth fix-up) of
-        the last global-loss step (waits for it)."""
+        the last global-loss step, or of the step `steps_back` (< 64) before it (waits for that step)."""
         ms = (C.c_float * 7)()
         with torch.cuda.device(self.device):
-            check(self.lib.be_ctx_last_train_timing(self.h, ms))
+            check(self.lib.be_ctx_train_timing_at(self.h, int(steps_back), ms))
         return list(ms)
 
     # ---- device-pointer entry points ---------------------------------------------------
@@ -427,17 +428,17 @@ class Context:
                 import torch.distributed as dist
                 if getattr(self, '_host_cnt', None) is None:
                     self._host_cnt = torch.zeros(2, device=self.device, dtype=torch.int64)
+                    self._host_cnt_B = torch.zeros(1, device=self.device, dtype=torch.int64)
                 cnt = self._host_cnt
-                # the global patch count is only known after the all-reduce, but every rank needs it for its kernels' scales: the
-                # patch counts travel first (host-side, 8 bytes), the mask count between the two halves
-                npatch = torch.tensor([B * self.L], dtype=torch.int64, device=self.device)
-                dist.all_reduce(npatch, group=process_group)
-                npatch = int(npatch.item())
-                check(self.lib.be_host_global_loss_begin(self.h, *hp, B, gam, npatch, int(grad is not None), C.c_void_p(cnt.data_ptr()),
+                # ONE 16-byte all-reduce of (mask count, patch count) between the two halves; the kernels are launched with the patch
+                # count the host can know (own patches x ranks) and `end` rescales if the shards turn out to be uneven
+                assumed = B * self.L * dist.get_world_size(process_group)
+                check(self.lib.be_host_global_loss_begin(self.h, *hp, B, gam, assumed, int(grad is not None), C.c_void_p(cnt.data_ptr()),
                                                          _stream(self.device)))
-                dist.all_reduce(cnt[:1], group=process_group)
-                check(self.lib.be_host_global_loss_end(self.h, B, gam, npatch, C.c_void_p(cnt.data_ptr()), C.c_void_p(terms.data_ptr()),
-                                                       C.c_void_p(loss.data_ptr()), gp, _stream(self.device)))
+                cnt[1:].fill_(B * self.L)
+                dist.all_reduce(cnt, group=process_group)
+                check(self.lib.be_host_global_loss_end(self.h, B, gam, assumed, C.c_void_p(cnt.data_ptr()), C.c_void_p(cnt.data_ptr() + 8),
+                                                       C.c_void_p(terms.data_ptr()), C.c_void_p(loss.data_ptr()), gp, _stream(self.device)))
         return terms, loss, grad
 
     # ---- host-buffer entry point (numpy / pinned host tensors in, numpy out) ------------

@@ -37,6 +37,8 @@ int fail(const char* fmt, ...) {
 
 constexpr int BE_HOST_CHUNKS = 16;  // maximum pipeline depth of the host-buffer entry point
 constexpr int BE_TRAIN_EVENTS = 10;
+constexpr int BE_TRAIN_SETS = 64;    // ring of event sets: the per-kernel times of the last 64 training steps can be read without a host
+                                     // synchronisation inside the timed loop
 
 struct be_ctx {
     be_config cfg;
@@ -73,7 +75,10 @@ struct be_ctx {
     // staging of be_host_global_loss (lazily allocated)
     float *ht_raw, *ht_ny, *ht_gt, *ht_bd, *ht_deri, *ht_zg, *ht_grad, *ht_gdep, *ht_scal;
     int ht_want_grad;
-    cudaEvent_t tev[BE_TRAIN_EVENTS];   // per-kernel timing of the last training step (be_ctx_last_train_timing)
+    cudaEvent_t tev_ring[BE_TRAIN_SETS][BE_TRAIN_EVENTS];
+    cudaEvent_t* tev;   // per-kernel timing: the event set of the current training step (be_ctx_last_train_timing / be_ctx_train_timing_at)
+    int tset;           // index of `tev` in the ring
+    long long tsteps;   // training steps timed since timing was enabled
     // deterministic fold (be_ctx_set_deterministic): per-patch-row slabs [max_batch][Hp][R][W][accw], allocated on first use
     int deterministic;
     float* stage;
@@ -238,7 +243,8 @@ int be_ctx_destroy(be_ctx* c) {
     cudaFree(c->gtable); cudaFree(c->T); cudaFree(c->partials); cudaFree(c->crec); cudaFree(c->lpart);
     cudaFree(c->ht_raw); cudaFree(c->ht_ny); cudaFree(c->ht_gt); cudaFree(c->ht_bd); cudaFree(c->ht_deri); cudaFree(c->ht_zg);
     cudaFree(c->ht_grad); cudaFree(c->ht_gdep); cudaFree(c->ht_scal);
-    for (int i = 0; i < BE_TRAIN_EVENTS; ++i) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
+    for (int k = 0; k < BE_TRAIN_SETS; ++k)
+        for (int i = 0; i < BE_TRAIN_EVENTS; ++i) if (c->tev_ring[k][i]) cudaEventDestroy(c->tev_ring[k][i]);
     cudaFree(c->blk_dev); cudaFreeHost(c->blk_pin);
     if (c->blk_ev) cudaEventDestroy(c->blk_ev);
     for (int i = 0; i < 3; ++i) if (c->st_streams[i]) cudaStreamDestroy(c->st_streams[i]);
@@ -267,6 +273,7 @@ int be_ctx_set_timing(be_ctx* c, int32_t enable) {
     if (enable && !c->ev[0])
         for (int i = 0; i < 5; ++i) BE_CUDA(cudaEventCreate(&c->ev[i]));
     c->timing = enable;
+    c->tsteps = 0;
     return 0;
 }
 
@@ -386,8 +393,11 @@ static int ensure_train_ws(be_ctx* c) {
 }
 
 static int ensure_train_events(be_ctx* c) {
-    if (c->tev[0]) return 0;
-    for (int i = 0; i < BE_TRAIN_EVENTS; ++i) BE_CUDA(cudaEventCreate(&c->tev[i]));
+    if (c->tev) return 0;
+    for (int k = 0; k < BE_TRAIN_SETS; ++k)
+        for (int i = 0; i < BE_TRAIN_EVENTS; ++i) BE_CUDA(cudaEventCreate(&c->tev_ring[k][i]));
+    c->tset = BE_TRAIN_SETS - 1;
+    c->tev = c->tev_ring[c->tset];
     return 0;
 }
 
@@ -450,6 +460,11 @@ static int global_loss_stage1_parts(be_ctx* c, const float* dev_raw, const float
         BE_CUDA(cudaMemsetAsync(dev_mask_count, 0, sizeof(int64_t), st));
         c->same_gt = (dev_img_gt == dev_img_ny);
         c->train_B = B;
+        if (c->timing) {                  // a new step: next event set of the ring
+            c->tset = (c->tset + 1) % BE_TRAIN_SETS;
+            c->tev = c->tev_ring[c->tset];
+            ++c->tsteps;
+        }
     } else {
         BE_REQUIRE(c->train_B == B, "be_global_loss_stage1_render must run first on the same batch");
     }
@@ -539,7 +554,7 @@ static int loss_stage2(be_ctx* c, int32_t B, const double* gammas7, int64_t glob
     cudaStream_t st = (cudaStream_t)stream;
     const BeGeom& g = c->g;
     const LossScales k = loss_scales(g, gammas7, global_patches);
-    const bool tm = c->timing != 0 && c->tev[0];
+    const bool tm = c->timing != 0 && c->tev;
     if (launch) {
         if (tm) cudaEventRecord(c->tev[6], st);
         if (loss_kernel_range(c, 0, B, B, k, dev_mask_count, dev_grad, dev_grad_depth, !finish, 0, &c->train_parts, st)) return 1;
@@ -576,14 +591,19 @@ int be_global_loss_stage2_finish(be_ctx* c, int32_t B, const double* gammas7, in
                        stream);
 }
 
-int be_ctx_last_train_timing(be_ctx* c, float* ms7) {
+int be_ctx_train_timing_at(be_ctx* c, int32_t steps_back, float* ms7) {
     if (check_ctx(c)) return 1;
-    BE_REQUIRE(ms7 && c->timing && c->tev[0], "timing is not enabled (be_ctx_set_timing) or no training step has run since");
-    BE_CUDA(cudaEventSynchronize(c->tev[9]));
+    BE_REQUIRE(ms7 && c->timing && c->tev && c->tsteps > 0, "timing is not enabled (be_ctx_set_timing) or no training step has run since");
+    BE_REQUIRE(steps_back >= 0 && steps_back < BE_TRAIN_SETS && steps_back < c->tsteps, "only the last %d timed steps are kept (asked for %d back of %lld)",
+               BE_TRAIN_SETS, steps_back, c->tsteps);
+    cudaEvent_t* ev = c->tev_ring[(c->tset - steps_back + BE_TRAIN_SETS) % BE_TRAIN_SETS];
+    BE_CUDA(cudaEventSynchronize(ev[9]));
     static const int from[7] = {0, 1, 2, 3, 4, 6, 8};
-    for (int i = 0; i < 7; ++i) BE_CUDA(cudaEventElapsedTime(&ms7[i], c->tev[from[i]], c->tev[from[i] + 1]));
+    for (int i = 0; i < 7; ++i) BE_CUDA(cudaEventElapsedTime(&ms7[i], ev[from[i]], ev[from[i] + 1]));
     return 0;
 }
+
+int be_ctx_last_train_timing(be_ctx* c, float* ms7) { return be_ctx_train_timing_at(c, 0, ms7); }
 
 // ---- host-buffer form of the training step (the e2e path of bench.py; what a ctypes binding on the reference side calls with numpy
 // arrays).  begin: H2D in chunks of pairs on an internal copy stream, per chunk stage 1 and the loss kernel with the depth normaliser
@@ -682,7 +702,7 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
 }
 
 int be_host_global_loss_end(be_ctx* c, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                            float* terms7, float* loss1, float* grad, void* stream) {
+                            const int64_t* dev_true_patches, float* terms7, float* loss1, float* grad, void* stream) {
     if (check_ctx(c)) return 1;
     BE_REQUIRE(gammas7 && dev_mask_count && terms7 && loss1, "null pointer");
     BE_REQUIRE(c->ht_raw && c->train_B == B && B > 0, "be_host_global_loss_begin must run first on the same batch");
@@ -692,12 +712,14 @@ int be_host_global_loss_end(be_ctx* c, int32_t B, const double* gammas7, int64_t
     cudaStream_t s_k = (cudaStream_t)stream;
     const LossScales k = loss_scales(g, gammas7, global_patches);
     float* d_terms = c->ht_scal;
-    be_launch_loss_reduce(c->partials, c->train_parts, k.sc, reinterpret_cast<const unsigned long long*>(dev_mask_count), nullptr, 0.0, d_terms,
-                          d_terms + 7, s_k);
+    const unsigned long long* tp = reinterpret_cast<const unsigned long long*>(dev_true_patches);
+    be_launch_loss_reduce(c->partials, c->train_parts, k.sc, reinterpret_cast<const unsigned long long*>(dev_mask_count), tp, (double)global_patches,
+                          d_terms, d_terms + 7, s_k);
     BE_CUDA(cudaMemcpyAsync(terms7, d_terms, 7 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
     BE_CUDA(cudaMemcpyAsync(loss1, d_terms + 7, sizeof(float), cudaMemcpyDeviceToHost, s_k));
     if (grad) {
-        be_launch_grad_depth_fixup(c->ht_grad, c->ht_gdep, reinterpret_cast<const unsigned long long*>(dev_mask_count), nullptr, 0.0, (size_t)B * L, s_k);
+        be_launch_grad_depth_fixup(c->ht_grad, c->ht_gdep, reinterpret_cast<const unsigned long long*>(dev_mask_count), tp, (double)global_patches,
+                                   (size_t)B * L, s_k);
         BE_CUDA(cudaMemcpyAsync(grad, c->ht_grad, (size_t)B * L * 12 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
     }
     BE_CUDA(cudaGetLastError());
@@ -713,7 +735,7 @@ int be_host_global_loss(be_ctx* c, const float* raw, const float* img_ny, const 
     int64_t* cnt = reinterpret_cast<int64_t*>(c->ht_scal + 8);
     const int64_t np_ = (int64_t)B * c->g.Hp * c->g.Wp;
     if (be_host_global_loss_begin(c, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, B, gammas7, np_, grad != nullptr, cnt, c->st_streams[1])) return 1;
-    return be_host_global_loss_end(c, B, gammas7, np_, cnt, terms7, loss1, grad, c->st_streams[1]);
+    return be_host_global_loss_end(c, B, gammas7, np_, cnt, nullptr, terms7, loss1, grad, c->st_streams[1]);
 }
 
 int be_local_loss(be_ctx* c, float* dev_est, const float* dev_img_ny, const float* dev_img_gt, const float* dev_bndry_dist,

@@ -173,7 +173,9 @@ int be_global_loss_stage2_finish(be_ctx* ctx, int32_t B, const double* gammas7, 
  *   be_host_global_loss            one call, one GPU.
  *   be_host_global_loss_begin/_end the two halves for data-parallel callers: `begin` leaves the local mask count in dev_mask_count
  *                                  (DEVICE int64, caller-owned) and issues its kernels on `stream`; the caller all-reduces the count
- *                                  over the ranks on that stream and passes the global patch count to both halves. */
+ *                                  over the ranks on that stream.  global_patches = (local patches) x (ranks) in both halves;
+ *                                  dev_true_patches (DEVICE int64 or NULL): the all-reduced true patch count, for uneven shards
+ *                                  (same correction as be_global_loss_stage2_finish). */
 int be_host_global_loss(be_ctx* ctx, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist,
                         const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, float* terms7, float* loss1,
                         float* grad);
@@ -181,7 +183,7 @@ int be_host_global_loss_begin(be_ctx* ctx, const float* raw, const float* img_ny
                               const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, int64_t global_patches,
                               int32_t want_grad, int64_t* dev_mask_count, void* stream);
 int be_host_global_loss_end(be_ctx* ctx, int32_t B, const double* gammas7, int64_t global_patches, const int64_t* dev_mask_count,
-                            float* terms7, float* loss1, float* grad, void* stream);
+                            const int64_t* dev_true_patches, float* terms7, float* loss1, float* grad, void* stream);
 
 /* LocalLoss.forward + backward (local_training.py:32-52) in ONE kernel launch: est [B,10] raw LocalStage output, img_ny / img_gt
  * [B,R,R,3], bndry_dist [B,R,R], deri [B,R-2,R-2,3] -> terms [3] = (colour, boundary localisation, smoothness),
@@ -250,6 +252,9 @@ int be_ctx_last_timing(be_ctx* ctx, float* ms4);
 /* The same for the training step (be_global_loss_stage1 + stage2, or stage2_launch + stage2_finish): ms7 = {accumulator memset,
  * be_setup_kernel, be_run3_kernel<TRAINFWD>, be_train_normalise_kernel, be_train_pack_kernel, be_loss2_kernel, reduce (+ depth fix-up)}. */
 int be_ctx_last_train_timing(be_ctx* ctx, float* ms7);
+/* the same for the step `steps_back` steps before the last one (a ring of 64 event sets: a benchmark loop reads the times of all
+ * its steps after the loop, without synchronising the host with the device between steps) */
+int be_ctx_train_timing_at(be_ctx* ctx, int32_t steps_back, float* ms7);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t be_launch_count(void);
