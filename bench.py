@@ -263,6 +263,21 @@ def _timed(fn, steps, warmup, dev, barrier, world, flush=None):
     return float(t.item())
 
 
+def _graph_of(fn, dev):
+    """fn captured into a CUDA graph after two warm-up calls on a side stream (collectives included: NCCL kernels are capturable)."""
+    cur, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        fn()
+        fn()
+    cur.wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
 def parity_checks(rank, world, dev):
     """N > 1 only: the sharded computations against the single-rank ones on the same global inputs (every rank can build all of
     them; the inputs are functions of the global sample index)."""
@@ -343,6 +358,14 @@ def extra_configs(args, rank, world, dev, barrier, flush):
 
         ms = _timed(val_step, steps, 3, dev, barrier, world, flush)
         out['train_step_batch32_total']['ms_per_step_distinct_noisy_and_clean_images'] = ms
+        if args.graphs:   # the same step (all-reduce included) replayed as one CUDA graph: what a captured training loop pays
+            try:
+                gr = _graph_of(strong_step, dev)
+                ms_g = _timed(gr.replay, steps, 3, dev, barrier, world, flush)
+                out['train_step_batch32_total'].update(ms_per_step_cuda_graph=ms_g, value_cuda_graph=32 * L / (ms_g / 1e3))
+                del gr
+            except Exception as e:
+                out['train_step_batch32_total']['cuda_graph_error'] = str(e)[:120]
         del crit, raw, ny, gt, bd, deri, zg
     # ---- deterministic fold mode (torch.use_deterministic_algorithms, global_training.py:177): cost of the fixed-order fold ----
     try:
@@ -461,6 +484,18 @@ def extra_configs(args, rank, world, dev, barrier, flush):
         ms_s = _timed(lambda: bh(est_b, big_img, gather=False), steps, 3, dev, barrier, world)
         out['big_1027'].update(collective='all_to_all of row bands (each rank owns 1/N of the image rows) + gather of the finished bands onto rank 0',
                                ms_per_image_maps_left_sharded_by_rows=ms_s, value_maps_left_sharded_by_rows=npatch_big / (ms_s / 1e3))
+    if args.graphs:       # at 8 ranks a rank renders 16 blocks in 0.18 ms: the ~15 host-side calls of the eager path take longer than that
+        try:
+            for key, kw in (('cuda_graph', {}), ('cuda_graph_sharded_by_rows', {'gather': False})):
+                if kw and world == 1:
+                    continue
+                gr = _graph_of(lambda: bh(est_b, big_img, **kw), dev)
+                ms_g = _timed(gr.replay, steps, 3, dev, barrier, world)
+                out['big_1027'][f'ms_per_image_{key}'] = ms_g
+                out['big_1027'][f'value_{key}'] = npatch_big / (ms_g / 1e3)
+                del gr
+        except Exception as e:
+            out['big_1027']['cuda_graph_error'] = str(e)[:120]
     return out
 
 
@@ -639,6 +674,7 @@ def main():
     ap.add_argument('--ref-pairs', type=int, default=1, help='pairs per step of the CPU reference sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (inference, densify w, big image, ...)')
+    ap.add_argument('--graphs', action='store_true', help='also time CUDA-graph replays of the communicating secondary configs')
     ap.add_argument('--no-numa', action='store_true', help='multi-rank runs: do not bind each rank to the CPUs of its GPU\'s NUMA node')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
