@@ -40,8 +40,10 @@ class GlobalLossFused(nn.Module):
       grad_reduce='sum': the rank's share is returned unscaled; the caller sums losses / gradients over the ranks itself.
     `last_loss_share` always holds the unscaled share."""
 
-    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None, grad_reduce='mean', deterministic=None):
+    def __init__(self, args, depthCal=None, device='cuda:0', process_group=None, grad_reduce='mean', deterministic=None,
+                 overlap_collective=True):
         super().__init__()
+        self.overlap_collective = bool(overlap_collective)
         self.deterministic = deterministic          # None: follow torch.are_deterministic_algorithms_enabled() (global_training.py:177)
         if grad_reduce not in ('mean', 'sum'):
             raise _lib.BlurryEdgesError(f"grad_reduce must be 'mean' or 'sum', got {grad_reduce!r}")
@@ -117,6 +119,13 @@ class GlobalLossFused(nn.Module):
         if self.process_group is None:
             gimg, gbnd, cnt = self.ctx.global_loss_stage1(*args)
             terms, loss, grad = self.ctx.global_loss_stage2(B, self.gammas(), npatch, cnt, want_grad)
+        elif not self.overlap_collective:
+            # plain recipe: the all-reduce sits between the two stages on the compute stream (its latency is exposed once per step)
+            from .dist_utils import sync_loss_normalisers
+            gimg, gbnd, cnt = self.ctx.global_loss_stage1(*args)
+            cnt, assumed = sync_loss_normalisers(cnt, npatch, self.process_group)
+            grad, gdep = self.ctx.global_loss_stage2_launch(B, self.gammas(), assumed, want_grad)
+            terms, loss, grad = self.ctx.global_loss_stage2_finish(B, self.gammas(), assumed, cnt, grad, gdep)
         else:
             # Normalisers of the WHOLE batch: one 16-byte all-reduce of (mask count, patch count).  It is started as soon as the render
             # kernels are queued (the count is final when they finish): the collective's kernel becomes resident while the small
