@@ -11,7 +11,7 @@ constexpr int BE_WARPS = BE_THREADS / 32;
 constexpr int BE_REC = 32;            // floats per patch-table record (128 B)
 constexpr int BE_ACC = 16;            // floats per pixel of the fold accumulator (15 used)
 constexpr int BE_GREC = 12;           // floats per patch of the backward chain-rule record
-constexpr int BE_CREC = 24;           // floats per patch of the colour record of the TRAINFWD pass: C[9] fp32, 3 pad, M^-1[6] as fp64 (packed 00,01,02,11,12,22)
+constexpr int BE_CREC = 16;           // floats per patch of the colour record of the TRAINFWD pass: C[9], M^-1[6] (packed 00,01,02,11,12,22)
 constexpr int BE_TW = 33;             // floats per pixel of the packed training targets: 8 float4 planes + 1 scalar plane (be_train.cu)
 
 enum BeRunMode { BE_RUN_COLORS = 0, BE_RUN_INFER = 1, BE_RUN_TRAINFWD = 2 };

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
     const size_t patch0 = ((size_t)b * g.Hp + py) * g.Wp + px0;
     const int np = 12;
 
-    // per-patch records: lanes 0-7 table, 8-10 gtable, 11-16 crec
+    // per-patch records: lanes 0-7 table, 8-10 gtable, 11-14 crec
     auto fetch = [&](size_t patch, int l) -> float4 {
         if (l < 8) return __ldg(reinterpret_cast<const float4*>(a.table + patch * BE_REC) + l);
         if (l < 8 + BE_GREC / 4) return __ldg(reinterpret_cast<const float4*>(a.gtable + patch * BE_GREC) + (l - 8));
@@ -190,17 +190,15 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
             AtG[0] = __shfl_sync(FULL, t4.x, 0); AtG[1] = __shfl_sync(FULL, t4.y, 0); AtG[2] = __shfl_sync(FULL, t4.z, 0);
             AtG[3] = __shfl_sync(FULL, t4.w, 0); AtG[4] = __shfl_sync(FULL, t4.x, 1); AtG[5] = __shfl_sync(FULL, t4.y, 1);
             AtG[6] = __shfl_sync(FULL, t4.z, 1); AtG[7] = __shfl_sync(FULL, t4.w, 1); AtG[8] = __shfl_sync(FULL, t4.x, 2);
-            {   // second solve of the ridge backward: V = M^-1 (A^T G), S = V C^T + C V^T, and the differences the render warps need -
-                // in fp64 (M^-1 comes in fp64 from the TRAINFWD record): both V and V_k - V_0 cancel, and this warp has the time
-                double C[9], Mi[6], V[9], Ssym[6];
-                const double* md = reinterpret_cast<const double*>(s_crec[cur] + 12);
+            {   // second solve of the ridge backward: V = M^-1 (A^T G), S = V C^T + C V^T (be_backsolve, fp32)
+                float C[9], Mi[6], V[9], Ssym[6];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) C[i] = (double)s_crec[cur][i];
+                for (int i = 0; i < 9; ++i) C[i] = s_crec[cur][i];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) Mi[i] = md[i];
+                for (int i = 0; i < 6; ++i) Mi[i] = s_crec[cur][9 + i];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const double b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
+                    const float b0 = AtG[c], b1 = AtG[3 + c], b2 = AtG[6 + c];
                     V[0 + c] = Mi[0] * b0 + Mi[1] * b1 + Mi[2] * b2;
                     V[3 + c] = Mi[1] * b0 + Mi[3] * b1 + Mi[4] * b2;
                     V[6 + c] = Mi[2] * b0 + Mi[4] * b1 + Mi[5] * b2;
@@ -208,16 +206,16 @@ __global__ void __launch_bounds__(NTHR, 2) be_loss2_kernel(const BeLossArgs a) {
                 const int pi_[6] = {0, 0, 0, 1, 1, 2}, pj_[6] = {0, 1, 2, 1, 2, 2};
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    double sacc = 0.0;
+                    float sacc = 0.0f;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) sacc += V[3 * pi_[i] + c] * C[3 * pj_[i] + c] + C[3 * pi_[i] + c] * V[3 * pj_[i] + c];
                     Ssym[i] = sacc;
                 }
                 if (lane == 0) {   // V_k - V_0 and S_k - S_0 (k = 1, 2): all the per-pixel backward needs (u_0 = 1 - u_1 - u_2)
                     float4* o = reinterpret_cast<float4*>(s_VS);
-                    o[0] = make_float4((float)(V[3] - V[0]), (float)(V[4] - V[1]), (float)(V[5] - V[2]), (float)(V[6] - V[0]));
-                    o[1] = make_float4((float)(V[7] - V[1]), (float)(V[8] - V[2]), (float)(Ssym[1] - Ssym[0]), (float)(Ssym[3] - Ssym[1]));
-                    o[2] = make_float4((float)(Ssym[4] - Ssym[2]), (float)(Ssym[2] - Ssym[0]), (float)(Ssym[4] - Ssym[1]), (float)(Ssym[5] - Ssym[2]));
+                    o[0] = make_float4(V[3] - V[0], V[4] - V[1], V[5] - V[2], V[6] - V[0]);
+                    o[1] = make_float4(V[7] - V[1], V[8] - V[2], Ssym[1] - Ssym[0], Ssym[3] - Ssym[1]);
+                    o[2] = make_float4(Ssym[4] - Ssym[2], Ssym[2] - Ssym[0], Ssym[4] - Ssym[1], Ssym[5] - Ssym[2]);
                 }
             }
             __syncwarp();

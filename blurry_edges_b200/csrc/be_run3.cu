@@ -171,14 +171,11 @@ __global__ void __launch_bounds__(NTHR, (MODE == BE_RUN_COLORS) ? 3 : 2) be_run3
                     col[1] = make_float4(C[3] - C[0], C[4] - C[1], C[5] - C[2], 0.0f);
                     col[2] = make_float4(C[6] - C[0], C[7] - C[1], C[8] - C[2], 0.0f);
                     if (TRAIN && a.crec != nullptr) {     // colours + M^-1 for the loss kernel (be_loss2.cu)
-                        // M^-1 stays fp64: the second solve of the backward pass, V = M^-1 (A^T G), and the differences V_k - V_0 cancel
-                        // (cond(M) ~ 200), and an fp32 M^-1 showed up as 1.6e-5 in the smoothness-only gradient
                         float4* cr = reinterpret_cast<float4*>(a.crec + (patch0 + k) * BE_CREC);
                         cr[0] = make_float4(C[0], C[1], C[2], C[3]);
                         cr[1] = make_float4(C[4], C[5], C[6], C[7]);
-                        cr[2] = make_float4(C[8], 0.0f, 0.0f, 0.0f);
-                        double2* md = reinterpret_cast<double2*>(a.crec + (patch0 + k) * BE_CREC + 12);
-                        md[0] = make_double2(Minv[0], Minv[1]); md[1] = make_double2(Minv[2], Minv[3]); md[2] = make_double2(Minv[4], Minv[5]);
+                        cr[2] = make_float4(C[8], (float)Minv[0], (float)Minv[1], (float)Minv[2]);
+                        cr[3] = make_float4((float)Minv[3], (float)Minv[4], (float)Minv[5], 0.0f);
                     }
                     if (INFER) {
                         const float* rec = s_rec + (k & 3) * BE_REC;
