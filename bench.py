@@ -516,7 +516,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     B = args.pairs
     from blurry_edges_b200.dist_utils import bind_to_gpu_numa_node
-    numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and not args.no_numa) else {'bound': False}
+    numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and args.numa) else {'bound': False}
     pg = dist.group.WORLD if world > 1 else None
     host = [t.contiguous().pin_memory() for t in train_inputs(B, rank * B, seed=200 + rank)]
     raw_h, ny_h, gt_h, bd_h, deri_h, zg_h = host
@@ -684,7 +684,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary configs (inference, densify w, big image, ...)')
     ap.add_argument('--graphs', action='store_true', help='also time CUDA-graph replays of the communicating secondary configs')
-    ap.add_argument('--no-numa', action='store_true', help='multi-rank runs: do not bind each rank to the CPUs of its GPU\'s NUMA node')
+    ap.add_argument('--numa', action='store_true', help='multi-rank runs: bind each rank to the CPUs NVML lists for its GPU (off by default: on the 8-GPU box it '
+                    'squeezed several ranks\' host threads onto few cores and cost 0.3 ms per step)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
