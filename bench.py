@@ -24,7 +24,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -71,16 +70,14 @@ def ncu_record(kernel):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 4 ms from a thread (the timed region of
-    the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as the fallback."""
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed regions, by the reporting rank only and INLINE from the loop that
+    issues the steps (`poll()` every few steps), not from a thread: a Python thread polling NVML every 4 ms made the polling rank's host
+    fall behind and, through the per-step collective, cost every other rank 0.7 ms per step at 8 GPUs (scratch/dp_instr.py: 2.85 ms
+    plain, 3.55 ms with the thread on rank 0).  The host runs a step ahead of the GPU, so an inline poll (~0.2 ms) costs nothing."""
 
     def __init__(self, index=0, active=True):
-        self.index, self.sm, self.mx, self.reasons, self.proc, self.stop = index, [], [], set(), None, False
-        self.rows = []
+        self.index, self.sm, self.mx, self.reasons, self.active = index, [], [], set(), active
         self.nvml = None
-        self.active = active
         if not active:
             return
         try:
@@ -93,83 +90,54 @@ class ClockSampler:
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.nvml = pynvml
-            # the first NVML queries of a process take milliseconds (longer when several ranks ask at once): pay for them here,
-            # not inside the timed region
-            pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
-            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.mx.append(int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)          # the first queries of a process are slow: pay here
             pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def poll(self):
+        if not self.active:
+            return
         n = self.nvml
+        if n is None:
+            try:
+                q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+                    'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+                r = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.sm.append(int(r[0])); self.mx.append(int(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:]):
+                    if v.strip().lower().startswith('active'):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            return
         bits = {'hw_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
                 'hw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
                 'sw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
                 'sw_power_cap': getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
         try:
-            self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
         except Exception:
             pass
-        while True:                               # at least one sample, the last one taken after `stop` was requested
-            last = self.stop
-            try:
-                self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            if last:
-                break
-            time.sleep(0.004)
 
     def __enter__(self):
-        if not self.active:
-            return self
-        if self.nvml is not None:
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-            return self
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20',
-                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
-
     def __exit__(self, *a):
-        self.stop = True
-        if not self.active:
-            return
-        if self.nvml is not None:
-            self.thread.join(timeout=2)
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        pass
 
     def summary(self):
-        if self.nvml is not None:
-            sm = sorted(self.sm)
-            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
-                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 4 ms period, over the device-resident and the e2e timed regions'}
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm), 'source': 'nvidia-smi'}
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': sorted(self.reasons), 'samples': len(sm),
+                'source': ('nvml' if self.nvml is not None else 'nvidia-smi') + ', polled inline by the reporting rank while the GPU works on the timed '
+                          'steps (every 4th step of the device-resident region)'}
 
 
 def restore_params(raw):
@@ -547,11 +515,13 @@ def run_ours(args, rank, world, local_rank):
     # kernel launches need too: measured at 8 GPUs, 3.26 ms per step with eight pollers against 2.86 ms with none (scratch/dp_modes.py).
     with ClockSampler(local_rank, active=(rank == 0)) as clk:
         t_wall = time.perf_counter()
-        for a, b in ev:
+        for i, (a, b) in enumerate(ev):
             flush.zero_()                                          # L2 flush between timed iterations (untimed)
             a.record()
             step()
             b.record()                                             # no host synchronisation between steps (a training loop has none)
+            if i % 4 == 1:
+                clk.poll()                                         # the GPU is busy with this step (and the queued ones) right now
         barrier()
         t_wall = time.perf_counter() - t_wall
         kern = [crit.ctx.last_train_timing(k) for k in range(min(args.steps, 64))]       # per-kernel CUDA events of the timed steps
@@ -567,7 +537,7 @@ def run_ours(args, rank, world, local_rank):
             crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, out=hout, process_group=pg)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for i in range(args.steps):
             crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, out=hout, process_group=pg)   # synchronises internally
         barrier()
         e2e_s = time.perf_counter() - t0
