@@ -72,7 +72,7 @@ def ncu_record(kernel):
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed regions, by the reporting rank only and INLINE from the loop that
     issues the steps (`poll()` every few steps), not from a thread: a Python thread polling NVML every 4 ms made the polling rank's host
-    fall behind and, through the per-step collective, cost every other rank 0.7 ms per step at 8 GPUs (scratch/dp_instr.py: 2.85 ms
+    fall behind and, through the per-step collective, cost every other rank 0.7 ms per step at 8 GPUs (tools/experiments/dp_instr.py: 2.85 ms
     plain, 3.55 ms with the thread on rank 0).  The host runs a step ahead of the GPU, so an inline poll (~0.2 ms) costs nothing."""
 
     def __init__(self, index=0, active=True):
@@ -512,7 +512,7 @@ def run_ours(args, rank, world, local_rank):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern = []
     # Only the rank that reports samples its GPU's clocks.  Eight processes polling NVML every 4 ms contend for a driver lock that
-    # kernel launches need too: measured at 8 GPUs, 3.26 ms per step with eight pollers against 2.86 ms with none (scratch/dp_modes.py).
+    # kernel launches need too: measured at 8 GPUs, 3.26 ms per step with eight pollers against 2.86 ms with none (tools/experiments/dp_modes.py).
     with ClockSampler(local_rank, active=(rank == 0)) as clk:
         t_wall = time.perf_counter()
         for i, (a, b) in enumerate(ev):
