@@ -1,7 +1,7 @@
 """Diagnostic: validation-call loss of the reference GlobalLoss (fp32 / fp64, on cuda:0) vs GlobalLossFused, with est from a
 xavier-initialised GlobalStage as global_training.py produces it."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.path.join(ROOT, 'baseline', '_ref', 'Blurry-Edges')
 sys.path[:0] = [os.path.join(ROOT, 'tests', '_stubs'), REF, ROOT, os.path.join(ROOT, 'tests')]
 import numpy as np, torch
