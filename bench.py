@@ -24,6 +24,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -70,74 +71,62 @@ def ncu_record(kernel):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed regions, by the reporting rank only and INLINE from the loop that
-    issues the steps (`poll()` every few steps), not from a thread: a Python thread polling NVML every 4 ms made the polling rank's host
-    fall behind and, through the per-step collective, cost every other rank 0.7 ms per step at 8 GPUs (tools/experiments/dp_instr.py: 2.85 ms
-    plain, 3.55 ms with the thread on rank 0).  The host runs a step ahead of the GPU, so an inline poll (~0.2 ms) costs nothing."""
+    """SM clock and throttle reasons sampled DURING the timed regions by a separate `nvidia-smi -lms 20` PROCESS watching the reporting
+    rank's GPU (started before the warm-up, so that its first sample is in before the timed region begins; rows are time-stamped by
+    a reader thread that sleeps in read()).  Nothing in the benchmark process itself talks to NVML while steps are being timed:
+    at 8 GPUs a Python thread polling NVML every 4 ms made the polling rank's host fall behind, and through the per-step
+    collective every other rank showed 3.55 ms per step instead of 2.85; five inline polls in 20 steps cost 1.4 ms per step
+    (tools/experiments/dp_instr.py, profiles/r2_experiments.txt)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0, active=True):
-        self.index, self.sm, self.mx, self.reasons, self.active = index, [], [], set(), active
-        self.nvml = None
+        self.index, self.active, self.rows, self.proc, self.t0, self.t1 = index, active, [], None, None, None
         if not active:
             return
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            try:
-                uuid = str(torch.cuda.get_device_properties(index).uuid)
-                uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
-                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
-            except Exception:
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.nvml = pynvml
-            self.mx.append(int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
-            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)          # the first queries of a process are slow: pay here
-            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            sel = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid           # CUDA_VISIBLE_DEVICES may renumber: select by UUID
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20', '-i', sel],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            t = time.perf_counter()
+            while not self.rows and time.perf_counter() - t < 5.0:              # nvidia-smi needs ~1 s to produce its first row
+                time.sleep(0.05)
         except Exception:
-            self.nvml = None
+            self.proc = None
 
-    def poll(self):
-        if not self.active:
-            return
-        n = self.nvml
-        if n is None:
-            try:
-                q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-                    'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-                r = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split(',')
-                self.sm.append(int(r[0])); self.mx.append(int(r[1]))
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:]):
-                    if v.strip().lower().startswith('active'):
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            return
-        bits = {'hw_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
-                'hw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
-                'sw_thermal_slowdown': getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
-                'sw_power_cap': getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
-        try:
-            self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-            for name, bit in bits.items():
-                if r & bit:
-                    self.reasons.add(name)
-        except Exception:
-            pass
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
 
     def __enter__(self):
+        self.t0 = time.perf_counter()
         return self
 
     def __exit__(self, *a):
-        pass
+        self.t1 = time.perf_counter()
+
+    def close(self):
+        if self.proc:
+            time.sleep(0.03)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
 
     def summary(self):
-        sm = sorted(self.sm)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
-                'reasons': sorted(self.reasons), 'samples': len(sm),
-                'source': ('nvml' if self.nvml is not None else 'nvidia-smi') + ', polled inline by the reporting rank while the GPU works on the timed '
-                          'steps (every 4th step of the device-resident region)'}
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.02]
+        used, where = (inside, 'inside') if inside else ([r for _, r in self.rows[-2:]], 'nearest to')
+        sm = sorted(int(r[0]) for r in used if r and r[0].isdigit())
+        mx = [int(r[1]) for r in used if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith('active') for r in used)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm),
+                'source': f'nvidia-smi -lms 20 in its own process on the reporting rank\'s GPU; samples {where} the device-resident + e2e timed regions'}
 
 
 def restore_params(raw):
@@ -504,6 +493,7 @@ def run_ours(args, rank, world, local_rank):
         raw.grad = None
         crit(raw, gt, gt, bd, deri, zg).backward()
 
+    clk = ClockSampler(local_rank, active=(rank == 0))            # its nvidia-smi process starts sampling now, before the warm-up
     crit.ctx.set_timing(True)
     for _ in range(args.warmup):
         step()
@@ -511,17 +501,13 @@ def run_ours(args, rank, world, local_rank):
     n0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern = []
-    # Only the rank that reports samples its GPU's clocks.  Eight processes polling NVML every 4 ms contend for a driver lock that
-    # kernel launches need too: measured at 8 GPUs, 3.26 ms per step with eight pollers against 2.86 ms with none (tools/experiments/dp_modes.py).
-    with ClockSampler(local_rank, active=(rank == 0)) as clk:
+    with clk:
         t_wall = time.perf_counter()
         for i, (a, b) in enumerate(ev):
             flush.zero_()                                          # L2 flush between timed iterations (untimed)
             a.record()
             step()
             b.record()                                             # no host synchronisation between steps (a training loop has none)
-            if i % 4 == 1:
-                clk.poll()                                         # the GPU is busy with this step (and the queued ones) right now
         barrier()
         t_wall = time.perf_counter() - t_wall
         kern = [crit.ctx.last_train_timing(k) for k in range(min(args.steps, 64))]       # per-kernel CUDA events of the timed steps
@@ -541,6 +527,7 @@ def run_ours(args, rank, world, local_rank):
             crit.ctx.host_global_loss(raw_h, gt_h, gt_h, bd_h, deri_h, zg_h, gammas, out=hout, process_group=pg)   # synchronises internally
         barrier()
         e2e_s = time.perf_counter() - t0
+    clk.close()
     # the two paths must agree on the result
     e2e_loss = float(hout[1].item())
     e2e_grad_err = float((hout[2].to(dev) - raw.grad / (world if pg is not None else 1)).abs().max() / (raw.grad.abs().max() / (world if pg is not None else 1)))
