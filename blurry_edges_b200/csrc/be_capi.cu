@@ -606,6 +606,9 @@ int be_ctx_train_timing_at(be_ctx* c, int32_t steps_back, float* ms7) {
 
 int be_ctx_last_train_timing(be_ctx* c, float* ms7) { return be_ctx_train_timing_at(c, 0, ms7); }
 
+static cudaEvent_t* g_trace_ev = nullptr;      // BE_HOST_TRACE: events of the last be_host_global_loss_begin
+static int g_trace_chunks = 0, g_trace_nb[BE_HOST_CHUNKS] = {0};
+
 // ---- host-buffer form of the training step (the e2e path of bench.py; what a ctypes binding on the reference side calls with numpy
 // arrays).  begin: H2D in chunks of pairs on an internal copy stream, per chunk stage 1 and the loss kernel with the depth normaliser
 // deferred, on the CALLER's stream (so that a data-parallel caller can all-reduce the count stream-ordered after it);
@@ -678,6 +681,10 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
         bounds[nw] = B;
     }
     int part_off = 0;
+    static const bool trace = getenv("BE_HOST_TRACE") != nullptr;       // timeline of one call on stderr (tuning aid)
+    static cudaEvent_t tev[3 * BE_HOST_CHUNKS + 2];
+    if (trace && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+    if (trace) { cudaEventRecord(tev[3 * BE_HOST_CHUNKS], s_in); g_trace_chunks = nchunk; }
     for (int i = 0; i < nchunk; ++i) {
         const int b0 = bounds[i], b1 = bounds[i + 1], nb = b1 - b0;
         if (nb <= 0) continue;
@@ -688,12 +695,15 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
         BE_CUDA(cudaMemcpyAsync(c->ht_deri + b0 * 6 * dHW, deri + b0 * 6 * dHW, nb * 6 * dHW * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaMemcpyAsync(c->ht_zg + b0 * HW, bndry_depth + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaEventRecord(c->st_events[i], s_in));
+        if (trace) cudaEventRecord(tev[3 * i], s_in);
         BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[i], 0));
         if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, dev_mask_count, s_k, false))
             return 1;
+        if (trace) cudaEventRecord(tev[3 * i + 1], s_k);
         int np_ = 0;
         if (loss_kernel_range(c, b0, nb, B, k, nullptr, want_grad ? c->ht_grad : nullptr, want_grad ? c->ht_gdep : nullptr, true, part_off, &np_, s_k))
             return 1;
+        if (trace) { cudaEventRecord(tev[3 * i + 2], s_k); g_trace_ev = tev; g_trace_nb[i] = nb; }
         part_off += np_;
     }
     c->train_parts = part_off;
@@ -724,7 +734,19 @@ int be_host_global_loss_end(be_ctx* c, int32_t B, const double* gammas7, int64_t
         BE_CUDA(cudaMemcpyAsync(grad, c->ht_grad, (size_t)B * L * 12 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
     }
     BE_CUDA(cudaGetLastError());
+    if (g_trace_ev) cudaEventRecord(g_trace_ev[3 * BE_HOST_CHUNKS + 1], s_k);
     BE_CUDA(cudaStreamSynchronize(s_k));
+    if (g_trace_ev) {
+        cudaEvent_t* tev = g_trace_ev;
+        float a, b2, d;
+        for (int i = 0; i < g_trace_chunks; ++i) {
+            cudaEventElapsedTime(&a, tev[3 * BE_HOST_CHUNKS], tev[3 * i]); cudaEventElapsedTime(&b2, tev[3 * BE_HOST_CHUNKS], tev[3 * i + 1]);
+            cudaEventElapsedTime(&d, tev[3 * BE_HOST_CHUNKS], tev[3 * i + 2]);
+            fprintf(stderr, "train chunk %d (%d pairs): h2d done %.3f  stage 1 done %.3f  loss kernel done %.3f ms\n", i, g_trace_nb[i], a, b2, d);
+        }
+        cudaEventElapsedTime(&a, tev[3 * BE_HOST_CHUNKS], tev[3 * BE_HOST_CHUNKS + 1]);
+        fprintf(stderr, "reduce + fix-up + d2h done %.3f ms\n", a);
+    }
     return 0;
 }
 
