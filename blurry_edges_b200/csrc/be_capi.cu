@@ -681,6 +681,15 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
         bounds[nw] = B;
     }
     int part_off = 0;
+    // Chunks alternate between the caller's stream and an internal one: the last, partly filled wave of chunk i's loss kernel then
+    // shares the GPU with chunk i+1's stage-1 kernels instead of leaving SMs idle (a chunk of n pairs is a whole number of waves
+    // only by accident).  The internal stream starts after the caller's stream reaches this call and is joined back at the end.
+    static const int nstreams = [] { const char* e = getenv("BE_HOST_TRAIN_STREAMS"); const int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+    cudaStream_t s_alt = c->st_streams[2];
+    if (nstreams == 2) {
+        BE_CUDA(cudaEventRecord(c->st_events[2 * BE_HOST_CHUNKS - 2], s_k));         // after the memset of the mask count
+        BE_CUDA(cudaStreamWaitEvent(s_alt, c->st_events[2 * BE_HOST_CHUNKS - 2], 0));
+    }
     static const bool trace = getenv("BE_HOST_TRACE") != nullptr;       // timeline of one call on stderr (tuning aid)
     static cudaEvent_t tev[3 * BE_HOST_CHUNKS + 2];
     if (trace && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
@@ -696,15 +705,20 @@ int be_host_global_loss_begin(be_ctx* c, const float* raw, const float* img_ny, 
         BE_CUDA(cudaMemcpyAsync(c->ht_zg + b0 * HW, bndry_depth + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
         BE_CUDA(cudaEventRecord(c->st_events[i], s_in));
         if (trace) cudaEventRecord(tev[3 * i], s_in);
-        BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[i], 0));
-        if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, dev_mask_count, s_k, false))
+        cudaStream_t s_c = (nstreams == 2 && (i & 1)) ? s_alt : s_k;
+        BE_CUDA(cudaStreamWaitEvent(s_c, c->st_events[i], 0));
+        if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, dev_mask_count, s_c, false))
             return 1;
-        if (trace) cudaEventRecord(tev[3 * i + 1], s_k);
+        if (trace) cudaEventRecord(tev[3 * i + 1], s_c);
         int np_ = 0;
-        if (loss_kernel_range(c, b0, nb, B, k, nullptr, want_grad ? c->ht_grad : nullptr, want_grad ? c->ht_gdep : nullptr, true, part_off, &np_, s_k))
+        if (loss_kernel_range(c, b0, nb, B, k, nullptr, want_grad ? c->ht_grad : nullptr, want_grad ? c->ht_gdep : nullptr, true, part_off, &np_, s_c))
             return 1;
-        if (trace) { cudaEventRecord(tev[3 * i + 2], s_k); g_trace_ev = tev; g_trace_nb[i] = nb; }
+        if (trace) { cudaEventRecord(tev[3 * i + 2], s_c); g_trace_ev = tev; g_trace_nb[i] = nb; }
         part_off += np_;
+    }
+    if (nstreams == 2) {                 // join: everything after this call on the caller's stream sees all chunks
+        BE_CUDA(cudaEventRecord(c->st_events[2 * BE_HOST_CHUNKS - 3], s_alt));
+        BE_CUDA(cudaStreamWaitEvent(s_k, c->st_events[2 * BE_HOST_CHUNKS - 3], 0));
     }
     c->train_parts = part_off;
     c->ht_want_grad = want_grad;
