@@ -35,6 +35,28 @@ for (R, stride, H, W) in ((21, 2, 29, 33), (11, 3, 26, 23)):
     crit(est, img, gt, bd, deri, zg).backward()
     torch.cuda.synchronize()
     print(f'R={R} stride={stride} {H}x{W}: maps {float(out[0].abs().sum()):.4f} colours {float(col.abs().sum()):.4f} grad {float(est.grad.abs().sum()):.6f}')
+    # round-2 paths: fixed-order fold (slabs + stage reduce), host-buffer training entry (two kernel streams), single-launch local loss
+    ctx.set_deterministic(True)
+    out_d = ctx.render_fold(raw, planar, _lib.planar_layout(H, W), param_mode=_lib.PARAMS_RAW12)
+    ctx.set_deterministic(False)
+    crit.deterministic = True
+    est2 = raw.clone().requires_grad_(True)
+    crit(est2, gt, gt, bd, deri, zg).backward()
+    crit.deterministic = False
+    ht = crit.ctx.host_global_loss(raw.cpu(), gt.cpu(), gt.cpu(), bd.cpu(), deri.cpu(), zg.cpu(), crit.gammas())
+    torch.cuda.synchronize()
+    print(f'  deterministic maps {float(out_d[0].abs().sum()):.4f} grad {float(est2.grad.abs().sum()):.6f} host loss {float(ht[1]):.6f}')
+largs = argparse.Namespace(R=21, w=1.0, alpha_lambda=5e-3, batch_size=8, mag=4.0, cam_params=cam, beta_bndry_loc=0.001, beta_smthns=0.0005,
+                           dynamic_epoch=200)
+lcrit = LocalLossFused(largs, 'cuda:0')
+lcrit.final_beta()
+le, lny, lgt, lbd, lderi = [t.cuda() for t in synth.local_batch(8, 21, seed=41)]
+leaf = le.clone().requires_grad_(True)
+for _ in range(2):                                   # twice: the ticket of the last-CTA reduction must have reset itself
+    leaf.grad = None
+    lcrit(leaf * 1.0, lny, lgt, lbd, lderi).backward()
+torch.cuda.synchronize()
+print(f'local loss grad {float(leaf.grad.abs().sum()):.6f} terms {lcrit.terms.tolist()}')
 x = torch.linspace(-5, 5, 1001, device='cuda', requires_grad=True)
 smish(x).sum().backward()
 torch.cuda.synchronize()
