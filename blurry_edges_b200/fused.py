@@ -62,6 +62,9 @@ class PostProcessFused(nn.Module):
 
     def _grow(self, B):
         if B > self.ctx.max_batch:
+            if torch.cuda.is_current_stream_capturing():      # a captured graph would keep pointers into the workspace freed here
+                raise _lib.BlurryEdgesError(f'batch of {B} pairs exceeds the context ({self.ctx.max_batch}) inside a CUDA-graph capture: '
+                                            'construct the helper with max_batch >= the largest batch')
             self.ctx.close()
             self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
 

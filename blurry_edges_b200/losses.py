@@ -107,6 +107,9 @@ class GlobalLossFused(nn.Module):
         if est.dim() != 3 or est.shape[1:] != (L, 12):
             raise _lib.BlurryEdgesError(f'expects est [B,{L},12], got {tuple(est.shape)}')
         if B > self.ctx.max_batch:
+            if torch.cuda.is_current_stream_capturing():      # a captured graph would keep pointers into the workspace freed here
+                raise _lib.BlurryEdgesError(f'batch of {B} pairs exceeds the context ({self.ctx.max_batch}) inside a CUDA-graph capture: '
+                                            'construct the criterion with batch_size >= the largest batch')
             self.ctx.close()
             self.ctx = _lib.Context(_lib.make_config(max_batch=B, **self._geo), self.device)
         raw = self._f32(est.detach())
