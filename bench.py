@@ -154,6 +154,18 @@ def loss_args(B):
 # CPU arm: the reference's eager fp32 path for the training step, restated (oracle/be_oracle.py + autograd; trace-formula inverse
 # as in utils/postprocessing_loss.py:104-112)
 # ---------------------------------------------------------------------------------------------------------------------
+def bench_config(B):
+    """`config` of the JSON line.  BOTH arms print this same dict (the reference arm measures a bounded sample of this workload and says
+    which in `cpu_baseline.sample`), so that the driver's same-config check of the two arms holds."""
+    return {'workload': f'GlobalLoss training step fwd+bwd (BASELINE.json configs[2]): {B} basic-shape {S}x{S} pairs per GPU = {B * L} '
+                        f'patches/step/GPU, R={R}, stride={STRIDE}, gamma_idx 0, est_raw = 0.1 N(0,1); scenes from the reference generator '
+                        '(tests/golden/shapes147.npz, 8 scenes round-robin)',
+            'call': 'criteria(est, img_gt, img_gt, bndry_dist, deri, bndry_depth) + backward (global_training.py:210-211)',
+            'l2': 'GPU arm: flushed between timed iterations (256 MiB write, untimed)',
+            'sharding': 'GPU arm: one 32-pair slice of the global batch per rank, 16-byte all-reduce of (mask count, patch count) inside the step; '
+                        'reference arm: rank 0 only, each step a bounded sample of the workload (cpu_baseline.sample)'}
+
+
 def cpu_train_step(inp, threads):
     from oracle import be_oracle as O
     raw, ny, gt, bd, deri, zg = inp
@@ -187,8 +199,7 @@ def run_reference(args, rank, world):
     out = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'GlobalLoss forward + autograd backward to est on {S}x{S} basic-shape pairs, R={R}, stride={STRIDE}; each step = '
-                                  f'{pairs} pair(s) ({pairs * L} patches), a bounded sample of the 32-pair batch of BASELINE configs[2]'},
+           'config': bench_config(args.pairs),
            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                             'sample': f'{pairs} pair(s)/step x {args.steps} steps after {args.warmup} warm-up steps, torch {torch.__version__} eager fp32 '
                                       'CPU + autograd, oracle/be_oracle.py restatement of the reference (timed within 3 % of the unmodified '
@@ -556,12 +567,7 @@ def run_ours(args, rank, world, local_rank):
     res = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
            'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'GlobalLoss training step fwd+bwd (BASELINE.json configs[2]): {B} basic-shape {S}x{S} pairs per GPU = {B * L} '
-                                  f'patches/step/GPU, R={R}, stride={STRIDE}, gamma_idx 0, est_raw = 0.1 N(0,1); scenes from the reference generator '
-                                  '(tests/golden/shapes147.npz, 8 scenes round-robin)',
-                      'call': 'criteria(est, img_gt, img_gt, bndry_dist, deri, bndry_depth) + backward (global_training.py:210-211)',
-                      'l2': 'flushed between timed iterations (256 MiB write, untimed)',
-                      'sharding': 'one 32-pair slice of the global batch per rank; 16-byte all-reduce of (mask count, patch count) inside the step'},
+           'config': bench_config(B),
            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(B * L * 12 * 4 + 32),
                    'ms_per_step': e2e_ms / args.steps,
                    'api': 'be_host_global_loss[_begin/_end] (pinned host buffers, synchronous): est, clean image pair (passed twice, copied once), '
@@ -610,6 +616,11 @@ def run_ours(args, rank, world, local_rank):
                                                              'note': 'the same torch restatement + autograd run eagerly on cuda:0 (fp32, 1 pair per step)'}
         except Exception as e:
             res['cpu_baseline']['eager_port_on_this_gpu'] = {'error': str(e)[:100]}
+    # The driver keeps the parsed contract keys plus the last ~1500 characters of the line: put what is NOT a contract key but carries the
+    # evidence (strong-scaling case, per-kernel times, the N>1 parity check) at the end.
+    for k in ('train_step_batch32_total', 'big_1027', 'kernel_ms', 'kernel_share_of_step', 'parity_check'):
+        if k in res:
+            res[k] = res.pop(k)
     _emit(res)
 
 

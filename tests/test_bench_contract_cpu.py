@@ -29,6 +29,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and 'model' not in d['config']
+    # both arms print the SAME config (the bounded sample the CPU arm times is named in cpu_baseline.sample)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config'] == bench.bench_config(32) and d['metric'] == bench.METRIC
+    assert 'pair' in d['cpu_baseline']['sample']
 
 
 def test_product_arm_refuses_to_run_without_a_gpu():
