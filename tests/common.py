@@ -59,3 +59,14 @@ def gloss_inputs(gname, kind, dt, B=2):
     img_gt, bd, deri, zgt = synth.loss_targets(B, S, S, seed=31, dtype=dt)
     raw = synth.raw_global(B, g.L, seed=33, kind=kind, dtype=dt)
     return g, raw, img_ny, img_gt, bd, deri, zgt
+
+
+def shapes_inference_inputs(dt):
+    """Inputs of tests/golden/shapes147_infer.npz (made by tests/golden/make_shapes_inference.py): the noisy pair of one full-size scene
+    of the reference's generator, est restored in fp32 as the script does, est10 for pass A."""
+    gold = Golden('shapes147_infer')
+    g = geom(147)
+    img = planar_pair(synth.shapes_batch(1, first=int(gold('scene')), dtype=dt)[0])                # [1,2,3,H,W]
+    est = O.restore_global(synth.raw_global(1, g.L, seed=83, dtype=F32)).to(dt)
+    est10 = synth.est_local(2, g.L, seed=85, dtype=dt)
+    return gold, g, est, est10, img

@@ -179,3 +179,18 @@ def test_oracle_on_basic_shape_scenes_of_the_reference_generator():
     (grad,) = torch.autograd.grad(loss, raw)
     assert abs(loss.item() - float(z['train.loss'])) <= 1e-10 * abs(loss.item())
     assert float((grad - torch.from_numpy(z['train.grad'])).abs().max()) <= 1e-9 * float(np.abs(z['train.grad']).max())
+
+
+def test_oracle_inference_on_a_generator_scene():
+    """tests/golden/shapes147_infer.npz: pass A and pass B of the unmodified blurry_edges_test.PostProcess (fp64) on the noisy pair of a
+    full-size basic-shape scene - hard edges, flat regions, the generator's noise model - under both mask rules."""
+    from common import shapes_inference_inputs
+    gold, g, est, est10, img = shapes_inference_inputs(F64)
+    assert relmax(O.colors_only(est10, img[0], g).numpy(), gold('passA')) < 1e-10
+    for densify in (None, 'w'):
+        ours = O.inference(est, img, g, CAM, 10.39, densify)
+        for name, o in zip(MAPS, ours):
+            key = f'{densify or "none"}/{name}' if name in ('refoc', 'depth', 'conf') else name
+            ref = gold(key)
+            assert o.shape == ref.shape, name
+            assert relmax(o.numpy(), ref) < 1e-9, (densify, name)
