@@ -570,7 +570,8 @@ def run_ours(args, rank, world, local_rank):
            'config': bench_config(B),
            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(B * L * 12 * 4 + 32),
                    'ms_per_step': e2e_ms / args.steps,
-                   'api': 'be_host_global_loss[_begin/_end] (pinned host buffers, synchronous): est, clean image pair (passed twice, copied once), '
+                   'api': ('be_host_global_loss (two-phase schedule' if world == 1 else 'be_host_global_loss_begin/_end (deferred normaliser, 16-byte all-reduce between the halves')
+                          + '; pinned host buffers, synchronous): est, clean image pair (passed twice, copied once), '
                           'bndry_dist, deri, bndry_depth in; terms, loss and grad est out',
                    'loss': e2e_loss, 'grad_max_err_vs_device_resident_path': e2e_grad_err, 'numa_binding_rank0': numa},
            'gpu_launches': int(launches),

@@ -405,10 +405,13 @@ class Context:
                                          C.c_void_p(loss.data_ptr()), _ptr(grad), _stream(self.device)))
         return terms, loss, grad
 
-    def host_global_loss(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, gammas, want_grad=True, out=None, process_group=None):
+    def host_global_loss(self, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, gammas, want_grad=True, out=None, process_group=None,
+                         deferred=False):
         """The training step on HOST tensors (CPU float32 contiguous, ideally pinned; dataset layouts of global_loss_stage1):
         -> (terms [7], loss [1], grad [B,L,12] | None) as CPU tensors (`out` = the same triple, reused).  With a process_group the
-        mask count and the patch count of the global batch are all-reduced between the two halves of the call."""
+        mask count and the patch count of the global batch are all-reduced between the two halves of the call
+        (be_host_global_loss_begin / _end: the depth normaliser is deferred); without one the two-phase schedule of be_host_global_loss
+        runs, which knows the count before the loss kernels start.  deferred=True forces the begin / end pair on a single process."""
         B = raw.shape[0]
         ts = (raw, img_ny, img_gt, bndry_dist, deri, bndry_depth)
         for t in ts:
@@ -422,7 +425,7 @@ class Context:
         hp = [C.c_void_p(t.data_ptr()) for t in ts]
         gp = C.c_void_p(grad.data_ptr()) if grad is not None else None
         with torch.cuda.device(self.device):
-            if process_group is None:
+            if process_group is None and not deferred:
                 check(self.lib.be_host_global_loss(self.h, *hp, B, gam, C.c_void_p(terms.data_ptr()), C.c_void_p(loss.data_ptr()), gp))
             else:
                 import torch.distributed as dist
@@ -432,11 +435,12 @@ class Context:
                 cnt = self._host_cnt
                 # ONE 16-byte all-reduce of (mask count, patch count) between the two halves; the kernels are launched with the patch
                 # count the host can know (own patches x ranks) and `end` rescales if the shards turn out to be uneven
-                assumed = B * self.L * dist.get_world_size(process_group)
+                assumed = B * self.L * (dist.get_world_size(process_group) if process_group is not None else 1)
                 check(self.lib.be_host_global_loss_begin(self.h, *hp, B, gam, assumed, int(grad is not None), C.c_void_p(cnt.data_ptr()),
                                                          _stream(self.device)))
                 cnt[1:].fill_(B * self.L)
-                dist.all_reduce(cnt, group=process_group)
+                if process_group is not None:
+                    dist.all_reduce(cnt, group=process_group)
                 check(self.lib.be_host_global_loss_end(self.h, B, gam, assumed, C.c_void_p(cnt.data_ptr()), C.c_void_p(cnt.data_ptr() + 8),
                                                        C.c_void_p(terms.data_ptr()), C.c_void_p(loss.data_ptr()), gp, _stream(self.device)))
         return terms, loss, grad

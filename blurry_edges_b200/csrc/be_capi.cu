@@ -764,11 +764,153 @@ int be_host_global_loss_end(be_ctx* c, int32_t B, const double* gammas7, int64_t
     return 0;
 }
 
+// Single-process form of the step on host buffers, two phases.  The depth term's normaliser is the mask count of the WHOLE batch
+// (global_training.py:127), which the device knows as soon as every chunk is rendered.  Phase 1 therefore renders chunk after chunk
+// behind the H2D copies of (est, image pair, z_gt); the copies of the loss-only inputs (bndry_dist, deri) follow on the same copy
+// stream.  Phase 2 packs the targets and runs the loss kernel per chunk with the FINAL count (no deferred normaliser, no fix-up pass),
+// so a chunk's gradient is final when its loss kernel ends and goes home while the next chunk's loss kernel runs: what is left after
+// the last kernel is the D2H of the last - smallest - chunk.  (The deferred form below, be_host_global_loss_begin/_end, stays for
+// data-parallel callers, whose count is only final after an all-reduce; it pays reduce + fix-up + the D2H of the whole gradient,
+// ~0.14 ms at 32 pairs, after the last kernel.)  BE_HOST_TRAIN_MODE=deferred selects the old schedule for comparison.
+static int host_global_loss_two_phase(be_ctx* c, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist,
+                                      const float* deri, const float* bndry_depth, int32_t B, const double* gammas7, float* terms7,
+                                      float* loss1, float* grad) {
+    BE_REQUIRE(raw && img_ny && img_gt && bndry_dist && deri && bndry_depth && gammas7 && terms7 && loss1, "null pointer");
+    BE_REQUIRE(B > 0 && B <= c->cfg.max_batch, "B=%d must be in [1, max_batch=%d]", B, c->cfg.max_batch);
+    BE_REQUIRE((double)B * c->g.H * c->g.W * BE_TW < 4.0e9, "batch of %d %dx%d pairs exceeds the 32-bit target offsets of the loss kernel", B, c->g.H, c->g.W);
+    const BeGeom& g = c->g;
+    const size_t HW = (size_t)g.H * g.W, L = (size_t)g.Hp * g.Wp, f = sizeof(float), dHW = (size_t)(g.H - 2) * (g.W - 2);
+    cudaStream_t s_in = c->st_streams[0], s_k = c->st_streams[1], s_alt = c->st_streams[2];
+    int64_t* cnt = reinterpret_cast<int64_t*>(c->ht_scal + 8);
+    const bool same = (img_gt == img_ny);
+    c->same_gt = same;
+    c->train_B = B;
+    const float* d_gt = same ? c->ht_ny : c->ht_gt;
+    const LossScales k = loss_scales(g, gammas7, (int64_t)B * (int64_t)L);
+    constexpr int MAXC = 8;                                  // events: [i] render inputs of chunk i, [8 + j] loss inputs of loss chunk j, [16 + j] loss kernel j done
+    // Phase 1 is paced by the copies (a pair's render inputs take about as long to arrive as the pair takes to render): a small first
+    // chunk, then equal ones.  The loss-only inputs follow in the order phase 2 consumes them; its first chunk is half the batch (those
+    // inputs are up when the last render ends), the last one is small (its gradient's way home is all that is left after the last kernel).
+    // Measured at 32 pairs: 3.02 ms per call against 3.20 ms for the deferred schedule (profiles/r2_experiments.txt).
+    static int wgt[MAXC] = {1, 3, 4, 4, 4}, wgt2[MAXC] = {8, 7, 1};
+    static int nw = 5, nw2 = 3;
+    static const bool parsed = [] {
+        auto parse = [](const char* name, int* w, int* n) {
+            const char* e = getenv(name);
+            if (!e) return;
+            int k = 0;
+            while (*e && k < MAXC) { const int v = atoi(e); w[k++] = v < 1 ? 1 : v; while (*e && *e != ',') ++e; if (*e == ',') ++e; }
+            if (k > 0) *n = k;
+        };
+        parse("BE_HOST_TRAIN_WGT", wgt, &nw);
+        parse("BE_HOST_TRAIN_WGT2", wgt2, &nw2);
+        return true;
+    }();
+    (void)parsed;
+    int bounds[MAXC + 1], bounds2[MAXC + 1];
+    auto split = [B](const int* w, int n, int* bd) {
+        int tot_w = 0, acc_w = 0;
+        for (int i = 0; i < n; ++i) tot_w += w[i];
+        bd[0] = 0;
+        for (int i = 0; i < n; ++i) { acc_w += w[i]; bd[i + 1] = (int)(((long long)B * acc_w + tot_w / 2) / tot_w); }
+        bd[n] = B;
+    };
+    split(wgt, nw, bounds);
+    split(wgt2, nw2, bounds2);
+    static const bool trace = getenv("BE_HOST_TRACE") != nullptr;
+    static cudaEvent_t tev[4 * MAXC + 2];
+    if (trace && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+    cudaEvent_t* ev = c->st_events;
+    BE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int64_t), s_k));
+    BE_CUDA(cudaEventRecord(ev[31], s_k));
+    BE_CUDA(cudaStreamWaitEvent(s_alt, ev[31], 0));
+    if (trace) cudaEventRecord(tev[4 * MAXC], s_in);
+    // ---- phase 1: render inputs up (small chunk first), render behind them; then the loss-only inputs (big chunk first) ----
+    for (int i = 0; i < nw; ++i) {
+        const int b0 = bounds[i], nb = bounds[i + 1] - b0;
+        if (nb <= 0) continue;
+        BE_CUDA(cudaMemcpyAsync(c->ht_raw + b0 * L * 12, raw + b0 * L * 12, nb * L * 12 * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_ny + b0 * 6 * HW, img_ny + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
+        if (!same) BE_CUDA(cudaMemcpyAsync(c->ht_gt + b0 * 6 * HW, img_gt + b0 * 6 * HW, nb * 6 * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_zg + b0 * HW, bndry_depth + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaEventRecord(ev[i], s_in));
+        cudaStream_t s_c = (i & 1) ? s_alt : s_k;
+        BE_CUDA(cudaStreamWaitEvent(s_c, ev[i], 0));
+        if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, cnt, s_c, false, 1)) return 1;
+        if (trace) { cudaEventRecord(tev[4 * i], s_in); cudaEventRecord(tev[4 * i + 1], s_c); }
+    }
+    for (int j = 0; j < nw2; ++j) {                          // loss-only inputs, in the order phase 2 consumes them
+        const int b0 = bounds2[j], nb = bounds2[j + 1] - b0;
+        if (nb <= 0) continue;
+        BE_CUDA(cudaMemcpyAsync(c->ht_bd + b0 * HW, bndry_dist + b0 * HW, nb * HW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaMemcpyAsync(c->ht_deri + b0 * 6 * dHW, deri + b0 * 6 * dHW, nb * 6 * dHW * f, cudaMemcpyHostToDevice, s_in));
+        BE_CUDA(cudaEventRecord(ev[8 + j], s_in));
+    }
+    // every chunk rendered = the mask count is final: both kernel streams wait for each other
+    BE_CUDA(cudaEventRecord(ev[30], s_alt));
+    BE_CUDA(cudaStreamWaitEvent(s_k, ev[30], 0));
+    BE_CUDA(cudaEventRecord(ev[29], s_k));
+    BE_CUDA(cudaStreamWaitEvent(s_alt, ev[29], 0));
+    // ---- phase 2: targets + loss kernel per chunk, gradient home behind each ----
+    // loss chunks alternate between the two kernel streams: the partly filled last wave of one shares the GPU with the start of the next
+    static const int streams2 = [] { const char* e = getenv("BE_HOST_TRAIN_STREAMS2"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    int part_off = 0;
+    for (int j = 0; j < nw2; ++j) {
+        const int b0 = bounds2[j], nb = bounds2[j + 1] - b0;
+        if (nb <= 0) continue;
+        cudaStream_t s_c = (streams2 == 2 && (j & 1)) ? s_alt : s_k;
+        BE_CUDA(cudaStreamWaitEvent(s_c, ev[8 + j], 0));
+        if (loss_stage1_range(c, c->ht_raw, c->ht_ny, d_gt, c->ht_bd, c->ht_deri, c->ht_zg, b0, nb, B, nullptr, nullptr, cnt, s_c, false, 2)) return 1;
+        int np_ = 0;
+        if (loss_kernel_range(c, b0, nb, B, k, cnt, grad ? c->ht_grad : nullptr, nullptr, false, part_off, &np_, s_c)) return 1;
+        part_off += np_;
+        if (trace) cudaEventRecord(tev[4 * j + 2], s_c);
+        if (grad) {
+            BE_CUDA(cudaEventRecord(ev[16 + j], s_c));
+            BE_CUDA(cudaStreamWaitEvent(s_in, ev[16 + j], 0));
+            BE_CUDA(cudaMemcpyAsync(grad + b0 * L * 12, c->ht_grad + b0 * L * 12, nb * L * 12 * f, cudaMemcpyDeviceToHost, s_in));
+            if (trace) cudaEventRecord(tev[4 * j + 3], s_in);
+        }
+    }
+    BE_CUDA(cudaEventRecord(ev[30], s_alt));
+    BE_CUDA(cudaStreamWaitEvent(s_k, ev[30], 0));
+    c->train_parts = part_off;
+    float* d_terms = c->ht_scal;
+    be_launch_loss_reduce(c->partials, part_off, k.sc, reinterpret_cast<const unsigned long long*>(cnt), nullptr, (double)B * (double)L, d_terms,
+                          d_terms + 7, s_k);
+    BE_CUDA(cudaMemcpyAsync(terms7, d_terms, 7 * sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    BE_CUDA(cudaMemcpyAsync(loss1, d_terms + 7, sizeof(float), cudaMemcpyDeviceToHost, s_k));
+    if (trace) cudaEventRecord(tev[4 * MAXC + 1], s_k);
+    BE_CUDA(cudaGetLastError());
+    BE_CUDA(cudaStreamSynchronize(s_k));
+    BE_CUDA(cudaStreamSynchronize(s_in));
+    if (trace) {
+        float a[2];
+        for (int i = 0; i < nw; ++i) {
+            if (bounds[i + 1] <= bounds[i]) continue;
+            cudaEventElapsedTime(&a[0], tev[4 * MAXC], tev[4 * i]); cudaEventElapsedTime(&a[1], tev[4 * MAXC], tev[4 * i + 1]);
+            fprintf(stderr, "render chunk %d (%d pairs): inputs up %.3f  rendered %.3f ms\n", i, bounds[i + 1] - bounds[i], a[0], a[1]);
+        }
+        for (int j = 0; j < nw2; ++j) {
+            if (bounds2[j + 1] <= bounds2[j]) continue;
+            a[1] = -1.f;
+            cudaEventElapsedTime(&a[0], tev[4 * MAXC], tev[4 * j + 2]);
+            if (grad) cudaEventElapsedTime(&a[1], tev[4 * MAXC], tev[4 * j + 3]);
+            fprintf(stderr, "loss chunk %d (%d pairs): loss kernel done %.3f  gradient home %.3f ms\n", j, bounds2[j + 1] - bounds2[j], a[0], a[1]);
+        }
+        cudaEventElapsedTime(&a[0], tev[4 * MAXC], tev[4 * MAXC + 1]);
+        fprintf(stderr, "reduce + terms home %.3f ms\n", a[0]);
+    }
+    return 0;
+}
+
 int be_host_global_loss(be_ctx* c, const float* raw, const float* img_ny, const float* img_gt, const float* bndry_dist, const float* deri,
                         const float* bndry_depth, int32_t B, const double* gammas7, float* terms7, float* loss1, float* grad) {
     if (check_ctx(c)) return 1;
     if (B == 0) return 0;
     if (ensure_train_ws(c) || ensure_train_staging(c)) return 1;
+    static const bool deferred = [] { const char* e = getenv("BE_HOST_TRAIN_MODE"); return e && !strcmp(e, "deferred"); }();
+    if (!deferred) return host_global_loss_two_phase(c, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, B, gammas7, terms7, loss1, grad);
     int64_t* cnt = reinterpret_cast<int64_t*>(c->ht_scal + 8);
     const int64_t np_ = (int64_t)B * c->g.Hp * c->g.Wp;
     if (be_host_global_loss_begin(c, raw, img_ny, img_gt, bndry_dist, deri, bndry_depth, B, gammas7, np_, grad != nullptr, cnt, c->st_streams[1])) return 1;

@@ -442,6 +442,24 @@ def test_host_buffer_training_entry_matches_the_device_path():
         assert none is None and hl2.item() == hl.item()
 
 
+@pytest.mark.parametrize('B', [1, 2, 3, 7])
+def test_host_buffer_training_entry_both_schedules_any_batch(B):
+    """The two schedules of the host-buffer step - two-phase (single process: final count before the loss kernels, gradient home per
+    chunk) and deferred (begin / end, what data-parallel callers use) - on batches smaller and larger than the number of chunks: both
+    equal the device-resident path."""
+    from blurry_edges_b200 import GlobalLossFused
+    g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('tiny', 'normal', F32, B=B)
+    crit = GlobalLossFused(_gargs(GEOMS['tiny'], B), None, 'cuda:0')
+    crit.update_gamma()
+    loss, grad, terms = _run_global(crit, raw, img_ny, img_gt, bd, deri, zgt)
+    for deferred in (False, True):
+        for _ in range(2):                                        # twice: the second call reuses staging buffers, events and streams
+            ht, hl, hg = crit.ctx.host_global_loss(raw, img_ny, img_gt, bd, deri, zgt, crit.gammas(), deferred=deferred)
+            np.testing.assert_allclose(ht.numpy(), terms, rtol=2e-6)
+            assert abs(hl.item() - loss) <= 2e-6 * abs(loss)
+            assert relmax(hg.numpy(), grad) < 2e-6, deferred
+
+
 def test_train_timing_hook_reports_the_seven_device_operations():
     from blurry_edges_b200 import GlobalLossFused
     g, raw, img_ny, img_gt, bd, deri, zgt = gloss_inputs('mid', 'normal', F32)
