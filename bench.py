@@ -555,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
     patches = B * L * world
     value = patches * args.steps / (dev_ms / 1e3)
     e2e = patches * args.steps / (e2e_ms / 1e3)
-    names = ['memset', 'be_setup_kernel', 'be_run3_kernel<TRAINFWD>', 'be_train_normalise_kernel', 'be_train_pack_kernel', 'be_loss2_kernel',
+    names = ['memset', 'be_setup_kernel', 'be_run3_kernel<TRAINFWD>', '(normalise: fused into be_train_targets_kernel)', 'be_train_targets_kernel', 'be_loss2_kernel',
              'reduce+fixup']
     shares = [sum(k[i] for k in kern) / len(kern) for i in range(7)]
     loss2_ms = shares[5]

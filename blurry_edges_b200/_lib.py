@@ -226,7 +226,8 @@ class Context:
         return list(ms)
 
     def last_train_timing(self, steps_back=0):
-        """ms of (memset, setup, be_run3_kernel<TRAINFWD>, train normalise, train pack, be_loss2_kernel, reduce + depth fix-up) of
+        """ms of (memset, setup, be_run3_kernel<TRAINFWD>, ~0 [slot of the former normalise launch], be_train_targets_kernel, be_loss2_kernel,
+        reduce + depth fix-up) of
         the last global-loss step, or of the step `steps_back` (< 64) before it (waits for that step)."""
         ms = (C.c_float * 7)()
         with torch.cuda.device(self.device):

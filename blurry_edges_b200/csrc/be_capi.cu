@@ -438,9 +438,11 @@ static int loss_stage1_range(be_ctx* c, const float* dev_raw, const float* dev_i
     }
     if (parts & 2) {   // targets: global maps + packed per-pixel targets of the loss kernel
         if (tm && !(parts & 1)) cudaEventRecord(c->tev[3], st);
-        be_launch_train_normalise(c->acc, g, b0, nb, Btot, c->T, dev_global_image, dev_global_bndry, st);
+        // one kernel: normalised global maps + packed per-pixel targets (the timing hook keeps its slot for the former normalise
+        // launch: it now reads ~0)
         if (tm) cudaEventRecord(c->tev[4], st);
-        be_launch_train_pack(g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T, st);
+        be_launch_train_targets(c->acc, g, b0, nb, Btot, dev_img_ny, dev_img_gt, dev_bndry_dist, dev_deri, dev_bndry_depth, c->T,
+                                dev_global_image, dev_global_bndry, st);
         if (tm) cudaEventRecord(c->tev[5], st);
     }
     BE_CUDA(cudaGetLastError());

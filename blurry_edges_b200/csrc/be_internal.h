@@ -93,9 +93,9 @@ struct BeLocalTail {                  // single-launch local loss: in-kernel set
 // launchers (be_kernels.cu / be_train.cu); all asynchronous on `st`
 void be_launch_setup(const float* est, int param_mode, int npatch, const BeCam& cam, float* table, float* gtable, cudaStream_t st);
 // pairs [b0, b0 + nb) of whole-batch arrays laid out for Btot pairs
-void be_launch_train_normalise(const float* acc, const BeGeom& g, int b0, int nb, int Btot, float* T, float* gimg, float* gbnd, cudaStream_t st);
-void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt, const float* bndry_dist,
-                          const float* deri, const float* bndry_depth, float* T, cudaStream_t st);
+void be_launch_train_targets(const float* acc, const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt,
+                             const float* bndry_dist, const float* deri, const float* bndry_depth, float* T, float* gimg, float* gbnd,
+                             cudaStream_t st);
 void be_launch_loss(const BeLossArgs& a, const BeLocalTail& tail, cudaStream_t st);   // local-stage loss, one launch (be_train.cu)
 void be_launch_loss2(const BeLossArgs& a, cudaStream_t st);              // global-stage loss (needs a.crec)
 void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsigned long long* mask_count, const unsigned long long* true_patches,

@@ -3,11 +3,10 @@
 //
 //   be_run3_kernel<TRAINFWD>  (be_run3.cu) renders both images + boundary and folds them -> accumulator [B,H,W,8],
 //                             counts the depth-term mask.
-//   be_train_normalise_kernel accumulator -> global image / boundary (detached targets, :154-155), written into the
-//                             packed per-pixel target record T[B,H,W,36] and, optionally, as planar tensors.
-//   be_train_pack_kernel      fills the rest of T: noisy + ground-truth pixels, log2(bndry_dist+1), z_gt, the
-//                             ground-truth derivative and Sobel(global image) (:106-110,117-118,123-124), so that the
-//                             loss kernel fetches everything about one pixel with nine 16-byte loads.
+//   be_train_targets_kernel   accumulator -> global image / boundary (detached targets, :154-155) and the packed per-pixel target
+//                             record T: noisy + ground-truth pixels, global image / boundary, log2(bndry_dist+1), z_gt, the
+//                             ground-truth derivative and Sobel(global image) (:106-110,117-118,123-124), so that the loss kernel
+//                             fetches everything about one pixel with a few 16-byte loads.
 //   be_local_loss_kernel      local-stage loss: one CTA per patch; phase 1 + ridge solve, render, direct dL/dP, Sobel forward
 //                             + adjoint through shared memory, A^T G + second solve, per-pixel backward to the per-patch
 //                             sums, chain rule to the 10 raw parameters.  (The global-stage loss is be_loss2.cu.)
@@ -54,34 +53,23 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
 // ---------------------------------------------------------------------------------------------------
 // Pairs [b0, b0 + nb) of a workspace laid out for Btot pairs (the host-buffer entry point runs the batch in chunks): `acc`, `T`,
 // `gimg`, `gbnd` are the arrays of the WHOLE batch, the plane stride of T is that of Btot pairs.
-__global__ void __launch_bounds__(256) be_train_normalise_kernel(const float* __restrict__ acc, BeGeom g, int b0, int nb, int Btot,
-                                                                 float* __restrict__ T, float* __restrict__ gimg,
-                                                                 float* __restrict__ gbnd) {
-    const size_t HW = (size_t)g.H * g.W;
-    const size_t lidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (lidx >= (size_t)nb * HW) return;
-    const size_t idx = lidx + (size_t)b0 * HW;
-    const size_t p = idx % HW;
-    const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
-    const float4* src = reinterpret_cast<const float4*>(acc + idx * 8);
-    const float4 q0 = src[0], q1 = src[1];
-    const float n = (float)(cover_1d(y, g.R, g.stride, g.Hp) * cover_1d(x, g.R, g.stride, g.Wp));
-    const float v[7] = {q0.x / n, q0.y / n, q0.z / n, q0.w / n, q1.x / n, q1.y / n, q1.z / n};
-    const size_t PS = (size_t)Btot * HW * 4;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) T[t_off(PS, idx, T_GI + c)] = v[c];
-    T[t_off(PS, idx, T_GB)] = v[6];
-    if (gimg) {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) gimg[((size_t)b * 6 + c) * HW + p] = v[c];
-    }
-    if (gbnd) gbnd[idx] = v[6];
+//
+// ONE kernel between the two passes (round 1 had two: normalise, then pack reading the normalised image back): a thread owns a pixel,
+// normalises its accumulator cell (fold / closed-form cover count, utils/postprocessing_loss.py:151-173) and - for the Sobel
+// magnitude of the global image (:114-117) - the cells of its 8 neighbours (same division, so the values are those the neighbours
+// write themselves; the 9 cells come from L1/L2), gathers the pixel's targets and writes the packed record as whole float4s (every
+// plane is stored once, 16 bytes per thread, instead of 33 scalar stores into 16-byte-strided planes).
+__device__ __forceinline__ void acc_pixel(const float* __restrict__ acc, size_t cell, float n, float (&v)[7]) {
+    const float4* src = reinterpret_cast<const float4*>(acc + cell * 8);
+    const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
+    v[0] = q0.x / n; v[1] = q0.y / n; v[2] = q0.z / n; v[3] = q0.w / n; v[4] = q1.x / n; v[5] = q1.y / n; v[6] = q1.z / n;
 }
 
-__global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int b0, int nb, int Btot, const float* __restrict__ img_ny,
-                                                            const float* __restrict__ img_gt, const float* __restrict__ bndry_dist,
-                                                            const float* __restrict__ deri, const float* __restrict__ bndry_depth,
-                                                            float* __restrict__ T) {
+__global__ void __launch_bounds__(256) be_train_targets_kernel(const float* __restrict__ acc, BeGeom g, int b0, int nb, int Btot,
+                                                               const float* __restrict__ img_ny, const float* __restrict__ img_gt,
+                                                               const float* __restrict__ bndry_dist, const float* __restrict__ deri,
+                                                               const float* __restrict__ bndry_depth, float* __restrict__ T,
+                                                               float* __restrict__ gimg, float* __restrict__ gbnd) {
     const bool same_gt = (img_gt == img_ny);          // the GT values are then never read (BeLossArgs::same_gt)
     const size_t HW = (size_t)g.H * g.W;
     const size_t lidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,35 +77,71 @@ __global__ void __launch_bounds__(256) be_train_pack_kernel(BeGeom g, int b0, in
     const size_t idx = lidx + (size_t)b0 * HW;
     const size_t p = idx % HW;
     const int b = (int)(idx / HW), y = (int)(p / g.W), x = (int)(p % g.W);
-    const size_t PS = (size_t)Btot * HW * 4;
+    const bool interior = (y >= 1 && y < g.H - 1 && x >= 1 && x < g.W - 1);
+    // cover counts of the three rows / columns around the pixel (separable)
+    float cy[3], cx[3];
+#pragma unroll
+    for (int o = -1; o <= 1; ++o) {
+        cy[o + 1] = (float)cover_1d(min(max(y + o, 0), g.H - 1), g.R, g.stride, g.Hp);
+        cx[o + 1] = (float)cover_1d(min(max(x + o, 0), g.W - 1), g.R, g.stride, g.Wp);
+    }
+    float v[7];
+    acc_pixel(acc, idx, cy[1] * cx[1], v);
+    float dgi[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dgt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (interior) {
+        // Sobel magnitude of the normalised global image, utils/postprocessing_loss.py:114-117
+        // row by row, so that only one row of neighbours is live: sx = (c - a) + 2 (f - d) + (i - g), sy = (a + 2 b + c) - (g + 2 h + i)
+        float sx[6], sy[6];
+#pragma unroll
+        for (int oi = -1; oi <= 1; ++oi) {
+            float l[7], m[7], r[7];
+            acc_pixel(acc, (size_t)((long long)idx + (long long)oi * g.W - 1), cy[oi + 1] * cx[0], l);
+            acc_pixel(acc, (size_t)((long long)idx + (long long)oi * g.W + 1), cy[oi + 1] * cx[2], r);
+            if (oi != 0) acc_pixel(acc, (size_t)((long long)idx + (long long)oi * g.W), cy[oi + 1] * cx[1], m);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                if (oi == -1) { sx[c] = r[c] - l[c]; sy[c] = l[c] + 2.0f * m[c] + r[c]; }
+                else if (oi == 0) sx[c] = sx[c] + 2.0f * (r[c] - l[c]);
+                else { sx[c] = sx[c] + (r[c] - l[c]); sy[c] = sy[c] - (l[c] + 2.0f * m[c] + r[c]); }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            dgi[c] = sqrtf(sx[c] * sx[c] + sy[c] * sy[c] + 1e-8f);
+            dgt[c] = deri[((((size_t)b * 2 + c / 3) * (g.H - 2) + (y - 1)) * (g.W - 2) + (x - 1)) * 3 + c % 3];
+        }
+    }
+    float ny[6], gt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const size_t o = (((size_t)b * 2 + m) * HW + p) * 3 + c;          // dataset-native [B,2,H,W,3]
-            T[t_off(PS, idx, T_NY + 3 * m + c)] = img_ny[o];
-            if (!same_gt) T[t_off(PS, idx, T_GT + 3 * m + c)] = img_gt[o];
+            ny[3 * m + c] = img_ny[o];
+            if (!same_gt) gt[3 * m + c] = img_gt[o];
         }
-    T[t_off(PS, idx, T_BD)] = log2f(bndry_dist[idx] + 1.0f);                  // global_training.py:118
-    T[t_off(PS, idx, T_ZG)] = bndry_depth[idx];
-    const bool interior = (y >= 1 && y < g.H - 1 && x >= 1 && x < g.W - 1);
-#pragma unroll
-    for (int mc = 0; mc < 6; ++mc) {
-        float dgt = 0.0f, dgi = 0.0f;
-        if (interior) {
-            const int m = mc / 3, c = mc % 3;
-            dgt = deri[((((size_t)b * 2 + m) * (g.H - 2) + (y - 1)) * (g.W - 2) + (x - 1)) * 3 + c];
-            // Sobel magnitude of the (already normalised) global image, utils/postprocessing_loss.py:114-117
-            const float* q = T + t_off(PS, idx, T_GI + mc);
-            const long long rs = (long long)g.W * 4, cs = 4;
-            const float a = q[-rs - cs], bb = q[-rs], cc = q[-rs + cs], d = q[-cs], f = q[cs], gg = q[rs - cs], hh = q[rs], ii = q[rs + cs];
-            const float sx = (cc - a) + 2.0f * (f - d) + (ii - gg);
-            const float sy = (a + 2.0f * bb + cc) - (gg + 2.0f * hh + ii);
-            dgi = sqrtf(sx * sx + sy * sy + 1e-8f);
-        }
-        T[t_off(PS, idx, T_DGT + mc)] = dgt;
-        T[t_off(PS, idx, T_DGI + mc)] = dgi;
+    const float bd = log2f(bndry_dist[idx] + 1.0f);                           // global_training.py:118
+    const size_t PS = (size_t)Btot * HW * 4;                                  // plane stride in floats
+    float4* t4 = reinterpret_cast<float4*>(T + idx * 4);
+    const size_t P4 = PS / 4;                                                 // ... in float4s
+    t4[0] = make_float4(ny[0], ny[1], ny[2], ny[3]);                          // values 0..3
+    if (same_gt) {
+        *reinterpret_cast<float2*>(t4 + P4) = make_float2(ny[4], ny[5]);      // values 4, 5 (6..11 are never read)
+    } else {
+        t4[P4] = make_float4(ny[4], ny[5], gt[0], gt[1]);                     // values 4..7
+        t4[2 * P4] = make_float4(gt[2], gt[3], gt[4], gt[5]);                 // values 8..11
     }
+    t4[3 * P4] = make_float4(v[0], v[1], v[2], v[3]);                         // global image 12..15
+    t4[4 * P4] = make_float4(v[4], v[5], v[6], bd);                           // 16, 17, global boundary 18, log2(bndry_dist + 1) 19
+    t4[5 * P4] = make_float4(dgt[0], dgt[1], dgt[2], dgt[3]);                 // 20..23
+    t4[6 * P4] = make_float4(dgt[4], dgt[5], dgi[0], dgi[1]);                 // 24..27
+    t4[7 * P4] = make_float4(dgi[2], dgi[3], dgi[4], dgi[5]);                 // 28..31
+    T[t_off(PS, idx, T_ZG)] = bndry_depth[idx];
+    if (gimg) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) gimg[((size_t)b * 6 + c) * HW + p] = v[c];
+    }
+    if (gbnd) gbnd[idx] = v[6];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -621,16 +645,12 @@ void be_launch_grad_depth_fixup(float* grad, const float* grad_depth, const unsi
     ++g_be_launches;
 }
 
-void be_launch_train_normalise(const float* acc, const BeGeom& g, int b0, int nb, int Btot, float* T, float* gimg, float* gbnd, cudaStream_t st) {
+void be_launch_train_targets(const float* acc, const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt,
+                             const float* bndry_dist, const float* deri, const float* bndry_depth, float* T, float* gimg, float* gbnd,
+                             cudaStream_t st) {
     const size_t n = (size_t)nb * g.H * g.W;
-    be_train_normalise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, b0, nb, Btot, T, gimg, gbnd);
-    ++g_be_launches;
-}
-
-void be_launch_train_pack(const BeGeom& g, int b0, int nb, int Btot, const float* img_ny, const float* img_gt, const float* bndry_dist,
-                          const float* deri, const float* bndry_depth, float* T, cudaStream_t st) {
-    const size_t n = (size_t)nb * g.H * g.W;
-    be_train_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, b0, nb, Btot, img_ny, img_gt, bndry_dist, deri, bndry_depth, T);
+    be_train_targets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, g, b0, nb, Btot, img_ny, img_gt, bndry_dist, deri, bndry_depth, T,
+                                                                         gimg, gbnd);
     ++g_be_launches;
 }
 

@@ -250,7 +250,8 @@ int be_eval_depth(be_ctx* ctx, const float* dev_depth, const float* dev_gt, int6
 int be_ctx_set_timing(be_ctx* ctx, int32_t enable);
 int be_ctx_last_timing(be_ctx* ctx, float* ms4);
 /* The same for the training step (be_global_loss_stage1 + stage2, or stage2_launch + stage2_finish): ms7 = {accumulator memset,
- * be_setup_kernel, be_run3_kernel<TRAINFWD>, be_train_normalise_kernel, be_train_pack_kernel, be_loss2_kernel, reduce (+ depth fix-up)}. */
+ * be_setup_kernel, be_run3_kernel<TRAINFWD>, ~0 (slot of the former separate normalise launch), be_train_targets_kernel (normalise + target
+ * packing in one launch), be_loss2_kernel, reduce (+ depth fix-up)}. */
 int be_ctx_last_train_timing(be_ctx* ctx, float* ms7);
 /* the same for the step `steps_back` steps before the last one (a ring of 64 event sets: a benchmark loop reads the times of all
  * its steps after the loop, without synchronising the host with the device between steps) */
